@@ -61,6 +61,8 @@ void ORACLE_PREFIX(prove_msms)(uint32_t nVars, uint32_t nPublic, uint32_t domain
 void ORACLE_PREFIX(blind)(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
                           const void *delta1, const void *delta2, const void *r32, const void *s32,
                           void *out_proof256);
+/* f2field.cpp:93-112 (Fq2 multiplication, 64-byte elements {a,b}) */
+void ORACLE_PREFIX(fq2_mul)(void *r, const void *a, const void *b);
 /* worker threads actually used (omp_get_max_threads for ref_, 1-or-omp for orc_) */
 int ORACLE_PREFIX(threads)(void);
 

@@ -122,6 +122,13 @@ void ref_g2_mul(void *r, const void *base, const void *scalar, uint32_t scalarSi
     memcpy(r, &pr, sizeof(pr));
 }
 
+void ref_fq2_mul(void *r, const void *a, const void *b)
+{
+    F2Element x, y, z; memcpy(&x, a, 64); memcpy(&y, b, 64);
+    F2.mul(z, x, y);
+    memcpy(r, &z, 64);
+}
+
 void ref_fr_fft(void *a, uint64_t n) { fft_for(n)->fft((FrElement *)a, n); }
 void ref_fr_ifft(void *a, uint64_t n) { fft_for(n)->ifft((FrElement *)a, n); }
 
