@@ -1,0 +1,127 @@
+/*
+ * b200snark.h - C-ABI of the B200-native Groth16 hot path (BN254).
+ *
+ * This is the drop-in boundary for the two hot paths inside the reference's
+ * Groth16::Prover<Engine>::prove (src/groth16.cpp:48-254):
+ *   - the multi-scalar multiplications   Curve::multiMulByScalar  (depends/ffiasm/c/curve.hpp:118-121
+ *                                        -> ParallelMultiexp::multiexp, depends/ffiasm/c/multiexp.cpp:98-144)
+ *   - the Fr-domain transforms           FFT<Field>::fft / ifft   (depends/ffiasm/c/fft.hpp:24-28,
+ *                                        fft.cpp:175-212)
+ *   - the fused H-polynomial pipeline + five MSMs of prove()      (src/groth16.cpp:52-207)
+ * Everything is plain pointers and sizes; no exceptions cross the boundary.
+ *
+ * Byte conventions (identical to the reference):
+ *   field element      32 B little-endian (4 x u64 == 8 x u32 limbs)
+ *   Fq / Fq2 / NTT data in Montgomery form, R = 2^256
+ *   G1 affine 64 B {x,y}; G2 affine 128 B {x.a,x.b,y.a,y.b}; (0,0) = point at infinity (curve.cpp:534-537)
+ *   G1 XYZZ 128 B {x,y,zz,zzz}; G2 XYZZ 256 B; zz == 0 = point at infinity (curve.hpp:11-16)
+ *   MSM scalars: plain (non-Montgomery) little-endian integers of `scalar_size` bytes, not reduced
+ *
+ * Return value: 0 = OK, non-zero = error (B200_ERR_*); text via b200_last_error().  All calls block
+ * until the result is in the caller's buffer.  One ctx is used by one host thread at a time (the
+ * reference's Prover is driven the same way: src/fullprover.cpp:84-99).
+ */
+#ifndef B200SNARK_H
+#define B200SNARK_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG 1     /* bad argument (null pointer, scalar_size > 32, n not a power of two, ...) */
+#define B200_ERR_CUDA 2    /* a CUDA runtime call or kernel failed */
+#define B200_ERR_NO_GPU 3  /* no usable CUDA device: the product path has NO CPU fallback */
+#define B200_ERR_RANGE 4   /* domain too big for the curve (fft.cpp:70-72) */
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_zkey b200_zkey;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int b200_init(int device, b200_ctx **out);
+void b200_free(b200_ctx *ctx);
+const char *b200_last_error(b200_ctx *ctx); /* ctx may be NULL: error of the last failed b200_init */
+/* kernels launched by this ctx since creation (bench.py's "gpu_launches") */
+uint64_t b200_launch_count(b200_ctx *ctx);
+/* device milliseconds (CUDA events on the ctx stream) of the last MSM / NTT / prove call, per phase;
+ * fills up to `cap` floats, returns how many; names via b200_phase_name(i) */
+int b200_last_phase_ms(b200_ctx *ctx, float *out, int cap);
+const char *b200_phase_name(int i);
+
+/* ---- MSM: replaces Curve::multiMulByScalar (curve.hpp:118-121) ---------------------------------- */
+/* host buffers in, XYZZ Montgomery out (any representative of the reference's result point) */
+int b200_msm_g1(b200_ctx *ctx, const void *bases_affine, const void *scalars, uint32_t scalar_size,
+                uint64_t n, void *out_xyzz128);
+int b200_msm_g2(b200_ctx *ctx, const void *bases_affine, const void *scalars, uint32_t scalar_size,
+                uint64_t n, void *out_xyzz256);
+/* same, bases and scalars already resident in device memory (raw device pointers) */
+int b200_msm_g1_dev(b200_ctx *ctx, const void *d_bases_affine, const void *d_scalars,
+                    uint32_t scalar_size, uint64_t n, void *out_xyzz128);
+int b200_msm_g2_dev(b200_ctx *ctx, const void *d_bases_affine, const void *d_scalars,
+                    uint32_t scalar_size, uint64_t n, void *out_xyzz256);
+/* window size override for experiments (0 = automatic) */
+void b200_set_msm_window(b200_ctx *ctx, int c_bits);
+
+/* ---- NTT: replaces FFT<Fr>::fft / ifft (fft.hpp:24-25), natural order in and out ------------------ */
+int b200_ntt_fr(b200_ctx *ctx, void *a_host, uint64_t n, int inverse);
+int b200_ntt_fr_dev(b200_ctx *ctx, void *d_a, uint64_t n, int inverse);
+
+/* ---- resident zkey + fused prove path (groth16.cpp:9-46 makeProver, :48-207 prove) ---------------- */
+typedef struct b200_zkey_desc {
+    uint32_t n_vars, n_public, domain_size;
+    uint64_t n_coefs;
+    const void *coefs;    /* zkey section 4 payload: u32 count, then n_coefs 44-byte records (groth16.hpp:27-35) */
+    const void *points_a; /* n_vars G1 */
+    const void *points_b1;/* n_vars G1 */
+    const void *points_b2;/* n_vars G2 */
+    const void *points_c; /* (n_vars - n_public - 1) G1 */
+    const void *points_h; /* domain_size G1 */
+    /* point-range shard owned by this ctx (multi-GPU): indices [shard_index*len/shard_count, ...) of
+     * every table; shard_count = 1 for a single GPU */
+    uint32_t shard_index, shard_count;
+} b200_zkey_desc;
+
+int b200_zkey_upload(b200_ctx *ctx, const b200_zkey_desc *desc, b200_zkey **out);
+void b200_zkey_free(b200_zkey *zk);
+/* a, b, c -> h scalars of groth16.cpp:52-163 (normal form, domain_size x 32 B) to a host buffer */
+int b200_h_scalars(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *h_out_host);
+/* H pipeline + this shard's part of the five MSMs of groth16.cpp:165-207.
+ * out768 = pih(128) pi_a(128) pib1(128) pi_b(256) pi_c(128), XYZZ Montgomery, pre-blinding */
+int b200_prove_msms(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *out768);
+
+/* ---- synthetic tables: k_i * G for known k_i (fixed-base, device side), affine Montgomery out ------ */
+int b200_fixed_base_g1(b200_ctx *ctx, const void *base_affine64, const void *scalars32, uint64_t n, void *out_affine);
+int b200_fixed_base_g2(b200_ctx *ctx, const void *base_affine128, const void *scalars32, uint64_t n, void *out_affine);
+
+/* ---- host-side group/field helpers (same arithmetic templates as the kernels, compiled for the CPU;
+ *      used for the O(1) blinding work of groth16.cpp:209-253 and to fold gathered partial results) --- */
+void b200_host_fq_mul(void *r, const void *a, const void *b);
+void b200_host_fq_add(void *r, const void *a, const void *b);
+void b200_host_fq_sub(void *r, const void *a, const void *b);
+void b200_host_fq_neg(void *r, const void *a);
+void b200_host_fq_inv(void *r, const void *a);
+void b200_host_fr_mul(void *r, const void *a, const void *b);
+void b200_host_fr_add(void *r, const void *a, const void *b);
+void b200_host_fr_sub(void *r, const void *a, const void *b);
+void b200_host_fr_neg(void *r, const void *a);
+void b200_host_fr_inv(void *r, const void *a);
+void b200_host_fq2_mul(void *r, const void *a, const void *b);
+void b200_host_fq2_sqr(void *r, const void *a);
+void b200_host_g1_add(void *r_xyzz, const void *a_xyzz, const void *b_xyzz);
+void b200_host_g1_madd(void *r_xyzz, const void *a_xyzz, const void *b_affine);
+void b200_host_g1_dbl(void *r_xyzz, const void *a_xyzz);
+void b200_host_g1_neg(void *r_xyzz, const void *a_xyzz);
+void b200_host_g1_to_affine(void *r_affine, const void *a_xyzz);
+void b200_host_g1_mul(void *r_xyzz, const void *base_affine, const void *scalar, uint32_t scalar_size);
+void b200_host_g2_add(void *r_xyzz, const void *a_xyzz, const void *b_xyzz);
+void b200_host_g2_madd(void *r_xyzz, const void *a_xyzz, const void *b_affine);
+void b200_host_g2_dbl(void *r_xyzz, const void *a_xyzz);
+void b200_host_g2_neg(void *r_xyzz, const void *a_xyzz);
+void b200_host_g2_to_affine(void *r_affine, const void *a_xyzz);
+void b200_host_g2_mul(void *r_xyzz, const void *base_affine, const void *scalar, uint32_t scalar_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

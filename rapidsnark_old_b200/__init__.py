@@ -1,0 +1,237 @@
+"""rapidsnark_old_b200 - B200-native Groth16 (BN254) hot path behind a C-ABI.
+
+This module is only the ctypes binding of ``include/b200snark.h`` (``libb200snark.so``, built from
+``csrc/`` by ``__graft_entry__.build()``).  The product is the CUDA library; there is no Python or CPU
+fallback: if the shared object is missing, or no CUDA device is present, the calls raise.
+
+Interface mirrored (reference iden3/rapidsnark-old):
+  Context.msm_g1 / msm_g2   <- Curve::multiMulByScalar      depends/ffiasm/c/curve.hpp:118-121
+  Context.ntt               <- FFT<Fr>::fft / ifft          depends/ffiasm/c/fft.hpp:24-25
+  Context.zkey_upload       <- Groth16::makeProver          src/groth16.cpp:9-46
+  ZKey.prove_msms           <- Prover::prove, pre-blinding  src/groth16.cpp:48-207
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200snark.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_NO_GPU, ERR_RANGE = 0, 1, 2, 3, 4
+
+_u32, _u64, _vp, _int = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int
+
+EXPORTS = [
+    "b200_init", "b200_free", "b200_last_error", "b200_launch_count", "b200_last_phase_ms", "b200_phase_name",
+    "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window",
+    "b200_ntt_fr", "b200_ntt_fr_dev",
+    "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms",
+    "b200_fixed_base_g1", "b200_fixed_base_g2",
+    "b200_host_fq_mul", "b200_host_fq_add", "b200_host_fq_sub", "b200_host_fq_neg", "b200_host_fq_inv",
+    "b200_host_fr_mul", "b200_host_fr_add", "b200_host_fr_sub", "b200_host_fr_neg", "b200_host_fr_inv",
+    "b200_host_fq2_mul", "b200_host_fq2_sqr",
+    "b200_host_g1_add", "b200_host_g1_madd", "b200_host_g1_dbl", "b200_host_g1_neg", "b200_host_g1_to_affine",
+    "b200_host_g1_mul",
+    "b200_host_g2_add", "b200_host_g2_madd", "b200_host_g2_dbl", "b200_host_g2_neg", "b200_host_g2_to_affine",
+    "b200_host_g2_mul",
+]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200snark error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ZKeyDesc(ctypes.Structure):
+    _fields_ = [("n_vars", _u32), ("n_public", _u32), ("domain_size", _u32), ("n_coefs", _u64),
+                ("coefs", _vp), ("points_a", _vp), ("points_b1", _vp), ("points_b2", _vp),
+                ("points_c", _vp), ("points_h", _vp), ("shard_index", _u32), ("shard_count", _u32)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built - there is nothing to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C rapidsnark_old_b200/csrc)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.b200_last_error.restype = ctypes.c_char_p
+        L.b200_last_error.argtypes = [_vp]
+        L.b200_phase_name.restype = ctypes.c_char_p
+        L.b200_launch_count.restype = _u64
+        L.b200_launch_count.argtypes = [_vp]
+        L.b200_init.argtypes = [_int, ctypes.POINTER(_vp)]
+        L.b200_free.argtypes = [_vp]
+        for name in ("b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev"):
+            getattr(L, name).argtypes = [_vp, _vp, _vp, _u32, _u64, _vp]
+        L.b200_set_msm_window.argtypes = [_vp, _int]
+        L.b200_ntt_fr.argtypes = [_vp, _vp, _u64, _int]
+        L.b200_ntt_fr_dev.argtypes = [_vp, _vp, _u64, _int]
+        L.b200_zkey_upload.argtypes = [_vp, ctypes.POINTER(ZKeyDesc), ctypes.POINTER(_vp)]
+        L.b200_zkey_free.argtypes = [_vp]
+        L.b200_h_scalars.argtypes = [_vp, _vp, _vp, _vp]
+        L.b200_prove_msms.argtypes = [_vp, _vp, _vp, _vp]
+        L.b200_fixed_base_g1.argtypes = [_vp, _vp, _vp, _u64, _vp]
+        L.b200_fixed_base_g2.argtypes = [_vp, _vp, _vp, _u64, _vp]
+        L.b200_last_phase_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), _int]
+        _lib = L
+    return _lib
+
+
+def _ptr(buf):
+    """bytes / bytearray / ctypes buffer / numpy array / int address -> void*"""
+    if isinstance(buf, int):
+        return _vp(buf)
+    if isinstance(buf, bytes):
+        return ctypes.cast(ctypes.c_char_p(buf), _vp)
+    if hasattr(buf, "ctypes"):
+        return _vp(buf.ctypes.data)
+    if isinstance(buf, bytearray):
+        return ctypes.cast((ctypes.c_char * len(buf)).from_buffer(buf), _vp)
+    return ctypes.cast(buf, _vp)
+
+
+# ----------------------------------------------------------------------------- host helpers (CPU)
+def _host_call(name, out_size, *args):
+    out = ctypes.create_string_buffer(out_size)
+    getattr(lib(), name)(out, *args)
+    return out.raw
+
+
+def host_g1_add(a, b): return _host_call("b200_host_g1_add", 128, a, b)
+def host_g2_add(a, b): return _host_call("b200_host_g2_add", 256, a, b)
+def host_g1_to_affine(a): return _host_call("b200_host_g1_to_affine", 64, a)
+def host_g2_to_affine(a): return _host_call("b200_host_g2_to_affine", 128, a)
+def host_g1_mul(base_affine, scalar): return _host_call("b200_host_g1_mul", 128, base_affine, scalar, _u32(len(scalar)))
+def host_g2_mul(base_affine, scalar): return _host_call("b200_host_g2_mul", 256, base_affine, scalar, _u32(len(scalar)))
+
+
+def fold_partials(parts768):
+    """Sum per-GPU partial results of prove_msms (pih, pi_a, pib1 | pi_b | pi_c) into one 768-byte record."""
+    acc = bytearray(parts768[0])
+    for p in parts768[1:]:
+        for off, size, add in ((0, 128, host_g1_add), (128, 128, host_g1_add), (256, 128, host_g1_add),
+                               (384, 256, host_g2_add), (640, 128, host_g1_add)):
+            acc[off:off + size] = add(bytes(acc[off:off + size]), bytes(p[off:off + size]))
+    return bytes(acc)
+
+
+# ----------------------------------------------------------------------------- device context
+class ZKey:
+    def __init__(self, ctx, handle, desc_keepalive):
+        self.ctx, self.handle, self._keep = ctx, handle, desc_keepalive
+        self.domain_size = desc_keepalive[0].domain_size
+
+    def h_scalars(self, wtns):
+        out = ctypes.create_string_buffer(self.domain_size * 32)
+        self.ctx._check(lib().b200_h_scalars(self.ctx.handle, self.handle, _ptr(wtns), out))
+        return out.raw
+
+    def prove_msms(self, wtns):
+        out = ctypes.create_string_buffer(768)
+        self.ctx._check(lib().b200_prove_msms(self.ctx.handle, self.handle, _ptr(wtns), out))
+        return out.raw
+
+    def free(self):
+        if self.handle:
+            lib().b200_zkey_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU, one stream (b200_ctx).  Raises B200Error(ERR_NO_GPU) when there is no CUDA device."""
+
+    def __init__(self, device=0):
+        h = _vp()
+        rc = lib().b200_init(device, ctypes.byref(h))
+        if rc != OK:
+            raise B200Error(rc, lib().b200_last_error(None).decode())
+        self.handle = h
+
+    def _check(self, rc):
+        if rc != OK:
+            raise B200Error(rc, lib().b200_last_error(self.handle).decode())
+
+    def close(self):
+        if self.handle:
+            lib().b200_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- MSM
+    def msm_g1(self, bases, scalars, n, scalar_size=32):
+        out = ctypes.create_string_buffer(128)
+        self._check(lib().b200_msm_g1(self.handle, _ptr(bases), _ptr(scalars), scalar_size, n, out))
+        return out.raw
+
+    def msm_g2(self, bases, scalars, n, scalar_size=32):
+        out = ctypes.create_string_buffer(256)
+        self._check(lib().b200_msm_g2(self.handle, _ptr(bases), _ptr(scalars), scalar_size, n, out))
+        return out.raw
+
+    def msm_g1_dev(self, d_bases, d_scalars, n, scalar_size=32):
+        out = ctypes.create_string_buffer(128)
+        self._check(lib().b200_msm_g1_dev(self.handle, _vp(d_bases), _vp(d_scalars), scalar_size, n, out))
+        return out.raw
+
+    def msm_g2_dev(self, d_bases, d_scalars, n, scalar_size=32):
+        out = ctypes.create_string_buffer(256)
+        self._check(lib().b200_msm_g2_dev(self.handle, _vp(d_bases), _vp(d_scalars), scalar_size, n, out))
+        return out.raw
+
+    def set_msm_window(self, c_bits):
+        lib().b200_set_msm_window(self.handle, c_bits)
+
+    # ---- NTT (natural order in/out, Montgomery data)
+    def ntt(self, data, inverse=False):
+        buf = ctypes.create_string_buffer(bytes(data), len(data))
+        self._check(lib().b200_ntt_fr(self.handle, buf, len(data) // 32, 1 if inverse else 0))
+        return buf.raw
+
+    def ntt_dev(self, d_ptr, n, inverse=False):
+        self._check(lib().b200_ntt_fr_dev(self.handle, _vp(d_ptr), n, 1 if inverse else 0))
+
+    # ---- zkey residency
+    def zkey_upload(self, n_vars, n_public, domain_size, n_coefs, coefs_section, points_a, points_b1, points_b2,
+                    points_c, points_h, shard_index=0, shard_count=1):
+        keep = [coefs_section, points_a, points_b1, points_b2, points_c, points_h]
+        d = ZKeyDesc(n_vars, n_public, domain_size, n_coefs, _ptr(coefs_section), _ptr(points_a), _ptr(points_b1),
+                     _ptr(points_b2), _ptr(points_c), _ptr(points_h), shard_index, shard_count)
+        h = _vp()
+        self._check(lib().b200_zkey_upload(self.handle, ctypes.byref(d), ctypes.byref(h)))
+        return ZKey(self, h, (d, keep))
+
+    # ---- synthetic tables
+    def fixed_base_g1(self, base_affine, scalars32, n):
+        out = ctypes.create_string_buffer(64 * max(n, 1))
+        self._check(lib().b200_fixed_base_g1(self.handle, _ptr(base_affine), _ptr(scalars32), n, out))
+        return out.raw[:64 * n]
+
+    def fixed_base_g2(self, base_affine, scalars32, n):
+        out = ctypes.create_string_buffer(128 * max(n, 1))
+        self._check(lib().b200_fixed_base_g2(self.handle, _ptr(base_affine), _ptr(scalars32), n, out))
+        return out.raw[:128 * n]
+
+    # ---- instrumentation
+    def launch_count(self):
+        return int(lib().b200_launch_count(self.handle))
+
+    def phase_ms(self):
+        arr = (ctypes.c_float * 16)()
+        k = lib().b200_last_phase_ms(self.handle, arr, 16)
+        return {lib().b200_phase_name(i).decode(): float(arr[i]) for i in range(k)}

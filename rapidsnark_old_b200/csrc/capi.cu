@@ -1,0 +1,120 @@
+// C-ABI entry points (include/b200snark.h): context management and the host-pointer / device-pointer
+// front ends of the MSM and NTT primitives.  No CPU fallback exists: without a CUDA device b200_init
+// fails with B200_ERR_NO_GPU.
+#include "ctx.cuh"
+
+using namespace b200;
+
+static std::string g_init_err;
+
+
+static const char *k_phase_names[PH_COUNT] = {"h2d", "msm_sort", "msm_accumulate", "msm_merge", "msm_reduce",
+                                              "msm_final", "build_abc", "ntt_h"};
+
+extern "C" {
+
+int b200_init(int device, b200_ctx **out) {
+    if (!out) return B200_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_init_err = std::string("b200_init: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path";
+        return B200_ERR_NO_GPU;
+    }
+    if (device < 0 || device >= ndev) {
+        g_init_err = "b200_init: device index out of range";
+        return B200_ERR_ARG;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_init_err = cudaGetErrorString(e); return B200_ERR_CUDA; }
+    b200_ctx *h = new b200_ctx();
+    h->c.device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_init_err = cudaGetErrorString(e); delete h; return B200_ERR_CUDA; }
+    *out = h;
+    return B200_OK;
+}
+
+void b200_free(b200_ctx *h) {
+    if (!h) return;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *all[] = {&c->w_hist, &c->w_cursor, &c->w_entries, &c->w_buckets, &c->w_partial, &c->w_hot,
+                     &c->w_scan_totals, &c->w_segs, &c->w_win, &c->w_in_bases, &c->w_in_scalars, &c->w_ntt};
+    for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (cudaEvent_t ev : c->evpool) cudaEventDestroy(ev);
+    ntt_free_tables(c);
+    cudaStreamDestroy(c->stream);
+    delete h;
+}
+
+const char *b200_last_error(b200_ctx *h) { return h ? h->c.err.c_str() : g_init_err.c_str(); }
+uint64_t b200_launch_count(b200_ctx *h) { return h ? h->c.launches : 0; }
+void b200_set_msm_window(b200_ctx *h, int c_bits) { if (h) h->c.force_c = c_bits; }
+
+int b200_last_phase_ms(b200_ctx *h, float *out, int cap) {
+    if (!h || !out) return 0;
+    int k = cap < PH_COUNT ? cap : PH_COUNT;
+    for (int i = 0; i < k; i++) out[i] = h->c.phase_ms[i];
+    return k;
+}
+const char *b200_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? k_phase_names[i] : ""; }
+
+// ---------------------------------------------------------------------------------------------- MSM
+static int msm_dev(b200_ctx *h, bool g2, const void *d_bases, const void *d_scalars, uint32_t scalar_size,
+                   uint64_t n, void *out) {
+    if (!h || !out) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    phase_reset(c);
+    int rc;
+    if (g2) { G2Xyzz r; rc = msm_g2_run(c, d_bases, d_scalars, scalar_size, n, &r); if (rc == B200_OK) memcpy(out, &r, sizeof r); }
+    else    { G1Xyzz r; rc = msm_g1_run(c, d_bases, d_scalars, scalar_size, n, &r); if (rc == B200_OK) memcpy(out, &r, sizeof r); }
+    cudaStreamSynchronize(c->stream);
+    phase_collect(c);
+    return rc;
+}
+
+static int msm_host(b200_ctx *h, bool g2, const void *bases, const void *scalars, uint32_t scalar_size,
+                    uint64_t n, void *out) {
+    if (!h || !out) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    if (n == 0) { memset(out, 0, g2 ? 256 : 128); return B200_OK; }
+    if (!bases || !scalars) { c->err = "msm: null input"; return B200_ERR_ARG; }
+    if (scalar_size == 0 || scalar_size > 32) { c->err = "msm: scalar_size must be 1..32 bytes"; return B200_ERR_ARG; }
+    size_t bsz = (size_t)n * (g2 ? 128 : 64), ssz = (size_t)n * scalar_size;
+    B200_TRY(ctx_reserve(c, c->w_in_bases, bsz));
+    B200_TRY(ctx_reserve(c, c->w_in_scalars, ssz + 64));
+    phase_reset(c);
+    phase_begin(c, PH_H2D);
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(c->w_in_bases.p, bases, bsz, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(c->w_in_scalars.p, scalars, ssz, cudaMemcpyHostToDevice, c->stream));
+    phase_end(c);
+    int rc;
+    if (g2) { G2Xyzz r; rc = msm_g2_run(c, c->w_in_bases.p, c->w_in_scalars.p, scalar_size, n, &r); if (rc == B200_OK) memcpy(out, &r, sizeof r); }
+    else    { G1Xyzz r; rc = msm_g1_run(c, c->w_in_bases.p, c->w_in_scalars.p, scalar_size, n, &r); if (rc == B200_OK) memcpy(out, &r, sizeof r); }
+    cudaStreamSynchronize(c->stream);
+    phase_collect(c);
+    return rc;
+}
+
+int b200_msm_g1(b200_ctx *h, const void *bases, const void *scalars, uint32_t scalar_size, uint64_t n, void *out) {
+    return msm_host(h, false, bases, scalars, scalar_size, n, out);
+}
+int b200_msm_g2(b200_ctx *h, const void *bases, const void *scalars, uint32_t scalar_size, uint64_t n, void *out) {
+    return msm_host(h, true, bases, scalars, scalar_size, n, out);
+}
+int b200_msm_g1_dev(b200_ctx *h, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, void *out) {
+    return msm_dev(h, false, d_bases, d_scalars, scalar_size, n, out);
+}
+int b200_msm_g2_dev(b200_ctx *h, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, void *out) {
+    return msm_dev(h, true, d_bases, d_scalars, scalar_size, n, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// Library context: one CUDA device, one stream, grow-only device workspaces, error text, phase timers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/b200snark.h"
+#include "curve.cuh"
+
+namespace b200 {
+
+enum Phase {
+    PH_H2D = 0,
+    PH_MSM_SORT,       // digits + histogram + scan + scatter
+    PH_MSM_ACCUM,      // bucket accumulation (dominant kernel)
+    PH_MSM_MERGE,      // boundary / hot bucket merge
+    PH_MSM_REDUCE,     // weighted bucket reduction + window sums
+    PH_MSM_FINAL,      // D2H of window sums + host Horner
+    PH_BUILD_AB,       // coefs x witness -> a, b, c
+    PH_NTT,            // the six transforms + twists + h combine
+    PH_COUNT
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    int force_c = 0;
+    float phase_ms[PH_COUNT] = {0};
+    struct Seg { int ph, e0, e1; };
+    std::vector<cudaEvent_t> evpool;   // phase timing events (reused call after call)
+    std::vector<Seg> segs;
+    int ev_used = 0;
+    std::vector<DevBuf *> bufs;  // everything to free
+
+    // MSM workspaces (shared by G1/G2 calls; grow-only)
+    DevBuf w_hist, w_cursor, w_entries, w_buckets, w_partial, w_hot, w_scan_totals, w_segs, w_win;
+    DevBuf w_in_bases, w_in_scalars;   // staging for host-pointer calls
+    DevBuf w_ntt;                      // staging for host-pointer NTT calls
+    void *pinned = nullptr;            // small pinned host buffer for results
+    size_t pinned_cap = 0;
+
+    // NTT twiddle tables (built lazily per log-size)
+    struct Twiddles;
+    Twiddles *tw = nullptr;
+};
+
+#define B200_CUDA_CHECK(ctx, call)                                                            \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            char b__[512];                                                                    \
+            snprintf(b__, sizeof b__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,           \
+                     cudaGetErrorString(e__));                                                \
+            (ctx)->err = b__;                                                                 \
+            return B200_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define B200_TRY(expr)                   \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != B200_OK) return rc__; \
+    } while (0)
+
+inline int ctx_reserve(Ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return B200_OK;
+    if (b.p) {
+        B200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        B200_CUDA_CHECK(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8;  // a little slack so a slightly larger next call does not realloc
+    B200_CUDA_CHECK(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return B200_OK;
+}
+
+inline int ctx_pinned(Ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return B200_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+    B200_CUDA_CHECK(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_cap = bytes;
+    return B200_OK;
+}
+
+// phase timers: CUDA events on the ctx stream around each phase; collected after the final sync
+inline int phase_event(Ctx *ctx) {
+    if (ctx->ev_used == (int)ctx->evpool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->evpool.push_back(e);
+    }
+    cudaEventRecord(ctx->evpool[ctx->ev_used], ctx->stream);
+    return ctx->ev_used++;
+}
+inline void phase_reset(Ctx *ctx) {
+    ctx->ev_used = 0;
+    ctx->segs.clear();
+    for (int i = 0; i < PH_COUNT; i++) ctx->phase_ms[i] = 0.f;
+}
+inline void phase_begin(Ctx *ctx, Phase ph) {
+    Ctx::Seg s;
+    s.ph = ph;
+    s.e0 = phase_event(ctx);
+    s.e1 = -1;
+    ctx->segs.push_back(s);
+}
+inline void phase_end(Ctx *ctx) { ctx->segs.back().e1 = phase_event(ctx); }
+inline void phase_collect(Ctx *ctx) {  // stream must be synchronized
+    for (auto &s : ctx->segs) {
+        if (s.e1 < 0) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->evpool[s.e0], ctx->evpool[s.e1]) == cudaSuccess) ctx->phase_ms[s.ph] += ms;
+    }
+    ctx->segs.clear();
+    ctx->ev_used = 0;
+}
+
+// launch bookkeeping: every kernel launch of ours goes through this macro
+#define B200_LAUNCH(ctx, kernel, grid, block, smem, ...)                            \
+    do {                                                                            \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+        (ctx)->launches++;                                                          \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            char b__[512];                                                          \
+            snprintf(b__, sizeof b__, "%s:%d: launch %s -> %s", __FILE__, __LINE__, \
+                     #kernel, cudaGetErrorString(e__));                             \
+            (ctx)->err = b__;                                                       \
+            return B200_ERR_CUDA;                                                   \
+        }                                                                           \
+    } while (0)
+
+void ntt_free_tables(Ctx *ctx);   // ntt.cu
+
+// msm entry points implemented in msm_g1.cu / msm_g2.cu
+int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G1Xyzz *out_host);
+int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G2Xyzz *out_host);
+
+}  // namespace b200
+
+// the opaque handle of include/b200snark.h
+struct b200_ctx {
+    b200::Ctx c;
+};

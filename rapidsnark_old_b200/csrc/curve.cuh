@@ -1,0 +1,170 @@
+// Short-Weierstrass a = 0 curve points in XYZZ coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2), written
+// once for G1 (F = Fq) and G2 (F = Fq2).
+//
+// Reference: ffiasm/c/curve.hpp:11-21 (Point{x,y,zz,zzz}, PointAffine{x,y}), curve.cpp:88-164 (add),
+// :182-248 (mixed add), :337-394 (dbl), :408-456 (dbl of an affine point), :529-537 (zero tests:
+// XYZZ zero <=> zz == 0, affine zero <=> (0,0)), :562-574 (to affine).  The formulas are the EFD
+// shortw-xyzz ones the reference names (add-2008-s, madd-2008-s, dbl-2008-s-1, mdbl-2008-s-1);
+// representatives may differ from the reference's, the affine value never does.
+#pragma once
+#include "fq2.cuh"
+
+namespace b200 {
+
+template <class F>
+struct alignas(16) Affine {
+    F x, y;
+    HD bool is_zero() const { return x.is_zero() && y.is_zero(); }
+};
+
+template <class F>
+struct alignas(16) Xyzz {
+    F x, y, zz, zzz;
+    HD bool is_zero() const { return zz.is_zero(); }
+    HD static Xyzz zero() {
+        Xyzz r;
+        r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero();
+        return r;
+    }
+    HD static Xyzz from_affine(const Affine<F> &p) {
+        Xyzz r;
+        if (p.is_zero()) return zero();
+        r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one();
+        return r;
+    }
+};
+
+typedef Affine<Fq> G1Affine;
+typedef Affine<Fq2> G2Affine;
+typedef Xyzz<Fq> G1Xyzz;
+typedef Xyzz<Fq2> G2Xyzz;
+
+// 2 * (affine p), p != 0     (mdbl-2008-s-1: 2M + 3S... here 3M + 3S with the W*y product)
+template <class F>
+HD_COLD Xyzz<F> ec_dbl_affine(const Affine<F> &p) {
+    Xyzz<F> r;
+    F u = fdbl(p.y);
+    F v = fsqr(u);
+    F w = fmul(u, v);
+    F s = fmul(p.x, v);
+    F xx = fsqr(p.x);
+    F m = fadd(fdbl(xx), xx);
+    r.x = fsub(fsqr(m), fdbl(s));
+    r.y = fsub(fmul(m, fsub(s, r.x)), fmul(w, p.y));
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+
+// 2 * p   (dbl-2008-s-1, a = 0)
+template <class F>
+HD_COLD Xyzz<F> ec_dbl(const Xyzz<F> &p) {
+    if (p.is_zero()) return p;
+    Xyzz<F> r;
+    F u = fdbl(p.y);
+    F v = fsqr(u);
+    F w = fmul(u, v);
+    F s = fmul(p.x, v);
+    F xx = fsqr(p.x);
+    F m = fadd(fdbl(xx), xx);
+    r.x = fsub(fsqr(m), fdbl(s));
+    r.y = fsub(fmul(m, fsub(s, r.x)), fmul(w, p.y));
+    r.zz = fmul(v, p.zz);
+    r.zzz = fmul(w, p.zzz);
+    return r;
+}
+
+// acc += q (q affine)   (madd-2008-s: 8M + 2S)
+template <class F>
+HD void ec_madd(Xyzz<F> &acc, const Affine<F> &q) {
+    if (q.is_zero()) return;
+    if (acc.is_zero()) {
+        acc.x = q.x; acc.y = q.y; acc.zz = F::one(); acc.zzz = F::one();
+        return;
+    }
+    F u2 = fmul(q.x, acc.zz);
+    F s2 = fmul(q.y, acc.zzz);
+    F p = fsub(u2, acc.x);
+    F r = fsub(s2, acc.y);
+    if (p.is_zero()) {
+        if (r.is_zero()) acc = ec_dbl_affine(q);   // same point
+        else acc = Xyzz<F>::zero();                 // opposite points
+        return;
+    }
+    F pp = fsqr(p);
+    F ppp = fmul(p, pp);
+    F qq = fmul(acc.x, pp);
+    F x3 = fsub(fsub(fsqr(r), ppp), fdbl(qq));
+    F y3 = fsub(fmul(r, fsub(qq, x3)), fmul(acc.y, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = fmul(acc.zz, pp);
+    acc.zzz = fmul(acc.zzz, ppp);
+}
+
+// acc += q   (add-2008-s: 12M + 2S)
+template <class F>
+HD_COLD void ec_add(Xyzz<F> &acc, const Xyzz<F> &q) {
+    if (q.is_zero()) return;
+    if (acc.is_zero()) { acc = q; return; }
+    F u1 = fmul(acc.x, q.zz);
+    F u2 = fmul(q.x, acc.zz);
+    F s1 = fmul(acc.y, q.zzz);
+    F s2 = fmul(q.y, acc.zzz);
+    F p = fsub(u2, u1);
+    F r = fsub(s2, s1);
+    if (p.is_zero()) {
+        if (r.is_zero()) acc = ec_dbl(acc);
+        else acc = Xyzz<F>::zero();
+        return;
+    }
+    F pp = fsqr(p);
+    F ppp = fmul(p, pp);
+    F qq = fmul(u1, pp);
+    F x3 = fsub(fsub(fsqr(r), ppp), fdbl(qq));
+    F y3 = fsub(fmul(r, fsub(qq, x3)), fmul(s1, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = fmul(fmul(acc.zz, q.zz), pp);
+    acc.zzz = fmul(fmul(acc.zzz, q.zzz), ppp);
+}
+
+template <class F>
+HD Xyzz<F> ec_neg(const Xyzz<F> &p) {
+    Xyzz<F> r = p;
+    r.y = fneg(p.y);
+    return r;
+}
+
+template <class F>
+HD Affine<F> ec_neg(const Affine<F> &p) {
+    Affine<F> r = p;
+    r.y = fneg(p.y);
+    return r;
+}
+
+// canonical affine value; infinity -> (0,0)   (curve.cpp:562-574)
+template <class F>
+HD Affine<F> ec_to_affine(const Xyzz<F> &p) {
+    Affine<F> r;
+    if (p.is_zero()) { r.x = F::zero(); r.y = F::zero(); return r; }
+    r.x = fmul(p.x, finv(p.zz));
+    r.y = fmul(p.y, finv(p.zzz));
+    return r;
+}
+
+// k * p for a little-endian scalar of nwords 32-bit words (plain double-and-add; O(1) per proof, used
+// by the host for blinding and by the device only for small bucket-index multipliers)
+template <class F>
+HD_COLD Xyzz<F> ec_mul(const Xyzz<F> &p, const u32 *k, int nwords) {
+    Xyzz<F> r = Xyzz<F>::zero();
+    int top = nwords * 32 - 1;
+    while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1)) top--;
+    for (int i = top; i >= 0; i--) {
+        r = ec_dbl(r);
+        if ((k[i >> 5] >> (i & 31)) & 1) ec_add(r, p);
+    }
+    return r;
+}
+
+}  // namespace b200

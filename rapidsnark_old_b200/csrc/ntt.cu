@@ -1,0 +1,377 @@
+// Fr-domain number-theoretic transforms and the H-polynomial pipeline on sm_100a.
+//
+// Replaces FFT<Fr>::fft / ifft (depends/ffiasm/c/fft.cpp:175-212; roots built by the ctor :32-115:
+// w_{2^s} = 5^((r-1)/2^s)).  The reference runs log2(n) full-array radix-2 passes after a bit-reverse
+// permutation (fft.cpp:159-171).  Here a transform of 2^k points is 2 (k <= 20) or 3 passes over HBM:
+// each pass keeps a tile of 2^S rows x 2^q adjacent columns in shared memory (two 16-byte planes per
+// element so 128-bit shared loads are conflict-free), runs S radix-2 butterfly stages on it with a
+// shared-memory copy of the 2^(S-1) local twiddles, and applies the inter-pass twiddle
+// w_M^(low * bitrev(row)) on the way in (DIT) or out (DIF).  Inter-pass twiddles and the coset twist
+// come from a two-level table of w_{2n} (2 x 2^14 entries instead of the reference's 2n-entry table,
+// fft.cpp:74-102).
+//   DIF passes: natural order in  -> bit-reversed out   (inverse transform of the H pipeline)
+//   DIT passes: bit-reversed in   -> natural out        (forward transform of the H pipeline)
+// so prove()'s ifft -> coset twist -> fft (src/groth16.cpp:101-155) needs no permutation pass at all;
+// the stand-alone b200_ntt_fr (natural in/out like the reference) adds one bit-reverse kernel.
+#include "ctx.cuh"
+#include "memops.cuh"
+
+namespace b200 {
+
+static const int NTT_LB = 14;        // low-table bits of the two-level root table
+static const int NTT_S_LAST = 11;    // max stages of the contiguous (lo = 0) pass: 2^11 x 32 B = 64 KB tile
+static const int NTT_S_STRIDED = 9;  // max stages of a strided pass (x 4 columns = 64 KB tile)
+static const int NTT_Q = 2;          // log2 columns of a strided tile: 4 x 32 B = one 128-byte line
+
+struct NttTable {
+    int s = 0;             // tables are powers of W = w_{2^s}
+    int loc_log = 0;       // loc[i] = w_{2^loc_log}^i, i < 2^(loc_log-1)
+    Fr *t_lo = nullptr;    // W^i, i < 2^LB
+    Fr *t_hi = nullptr;    // W^(i << LB)
+    Fr *loc = nullptr;
+};
+
+struct Ctx::Twiddles {
+    // index [s][inverse]
+    NttTable tab[29][2];
+};
+
+DEVFN Fr lds_fr(const uint4 *p0, const uint4 *p1, u32 i) {
+    Fr r;
+    uint4 a = p0[i], b = p1[i];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+DEVFN void sts_fr(uint4 *p0, uint4 *p1, u32 i, const Fr &r) {
+    p0[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    p1[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// W^e from the two-level table
+DEVFN Fr root_pow(const Fr *__restrict__ t_lo, const Fr *__restrict__ t_hi, int s, u32 e) {
+    Fr lo = ldg_struct(t_lo + (e & ((1u << NTT_LB) - 1)));
+    if (s <= NTT_LB) return lo;
+    Fr hi = ldg_struct(t_hi + (e >> NTT_LB));
+    return fp_mul(lo, hi);
+}
+
+// build tables: out[i] = base^(i * stride_mul) for i < count, base given in Montgomery form
+__global__ void __launch_bounds__(256) k_ntt_build_powers(Fr base, u32 count, Fr *__restrict__ out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr r = Fr::one(), b = base;
+    for (u32 e = i; e != 0; e >>= 1) {
+        if (e & 1) r = fp_mul(r, b);
+        b = fp_sqr(b);
+    }
+    st_struct(out + i, r);
+}
+
+template <bool DIT>
+__global__ void __launch_bounds__(512) k_ntt_pass(Fr *__restrict__ a, int lo, int S, int q, NttTable tb) {
+    extern __shared__ uint4 smem_raw[];
+    const u32 R = 1u << S, Q = 1u << q, tile_elems = R << q;
+    uint4 *x0 = smem_raw, *x1 = x0 + tile_elems;
+    uint4 *w0 = x1 + tile_elems, *w1 = w0 + (R >> 1);
+
+    const u32 tiles_per_group = 1u << (lo - q);
+    const u32 tile = blockIdx.x;
+    const u64 base = (u64)(tile >> (lo - q)) << (lo + S);
+    const u32 l0 = (tile & (tiles_per_group - 1)) << q;
+    const int tw_shift = tb.s - (lo + S);   // w_M = W^(2^tw_shift)
+
+    for (u32 i = threadIdx.x; i < (R >> 1); i += blockDim.x) {
+        Fr w = ldg_struct(tb.loc + ((size_t)i << (tb.loc_log - S)));
+        sts_fr(w0, w1, i, w);
+    }
+    for (u32 e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+        u32 r = e >> q, c = e & (Q - 1);
+        Fr x = ld_struct(a + base + ((u64)r << lo) + l0 + c);
+        if (DIT && lo > 0) {
+            u32 k1 = __brev(r) >> (32 - S);
+            u32 ex = ((l0 + c) * k1) << tw_shift;
+            if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
+        }
+        sts_fr(x0, x1, e, x);
+    }
+    __syncthreads();
+
+    const u32 nbf = tile_elems >> 1;   // butterflies per stage
+    if (DIT) {
+        for (u32 half = 1; half < R; half <<= 1) {
+            const u32 tw_mul = (R >> 1) / half;
+            for (u32 id = threadIdx.x; id < nbf; id += blockDim.x) {
+                u32 c = id & (Q - 1), t = id >> q;
+                u32 pos = t & (half - 1), grp = t / half;
+                u32 r0 = grp * 2 * half + pos;
+                u32 i0 = (r0 << q) + c, i1 = i0 + (half << q);
+                Fr u = lds_fr(x0, x1, i0), v = lds_fr(x0, x1, i1);
+                if (pos) v = fp_mul(v, lds_fr(w0, w1, pos * tw_mul));
+                sts_fr(x0, x1, i0, fp_add(u, v));
+                sts_fr(x0, x1, i1, fp_sub(u, v));
+            }
+            __syncthreads();
+        }
+    } else {
+        for (u32 half = R >> 1; half >= 1; half >>= 1) {
+            const u32 tw_mul = (R >> 1) / half;
+            for (u32 id = threadIdx.x; id < nbf; id += blockDim.x) {
+                u32 c = id & (Q - 1), t = id >> q;
+                u32 pos = t & (half - 1), grp = t / half;
+                u32 r0 = grp * 2 * half + pos;
+                u32 i0 = (r0 << q) + c, i1 = i0 + (half << q);
+                Fr u = lds_fr(x0, x1, i0), v = lds_fr(x0, x1, i1);
+                Fr d = fp_sub(u, v);
+                if (pos) d = fp_mul(d, lds_fr(w0, w1, pos * tw_mul));
+                sts_fr(x0, x1, i0, fp_add(u, v));
+                sts_fr(x0, x1, i1, d);
+            }
+            __syncthreads();
+        }
+    }
+
+    for (u32 e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+        u32 r = e >> q, c = e & (Q - 1);
+        Fr x = lds_fr(x0, x1, e);
+        if (!DIT && lo > 0) {
+            u32 k1 = __brev(r) >> (32 - S);
+            u32 ex = ((l0 + c) * k1) << tw_shift;
+            if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
+        }
+        st_struct(a + base + ((u64)r << lo) + l0 + c, x);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ntt_bitrev(Fr *__restrict__ a, int k) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> k) return;
+    u64 j = (u64)(__brevll(i) >> (64 - k));
+    if (i < j) {
+        Fr x = ld_struct(a + i), y = ld_struct(a + j);
+        st_struct(a + i, y);
+        st_struct(a + j, x);
+    }
+}
+
+// a[i] *= f   (ifft tail: x powTwoInv, fft.cpp:206-211)
+__global__ void __launch_bounds__(256) k_ntt_scale(Fr *__restrict__ a, u64 n, Fr f) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_struct(a + i, fp_mul(ld_struct(a + i), f));
+}
+
+// after the inverse DIF passes position p holds coefficient bitrev(p): scale by 1/n and apply the coset
+// twist w_{2n}^bitrev(p)  (groth16.cpp:107-110 with fft.hpp:28 root(domainPower+1, i))
+__global__ void __launch_bounds__(256) k_ntt_scale_twist_brev(Fr *__restrict__ a, int k, Fr n_inv, NttTable tb) {
+    u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >> k) return;
+    u32 i = k ? (u32)(__brevll(p) >> (64 - k)) : 0;
+    u32 ex = i << (tb.s - (k + 1));
+    Fr x = fp_mul(ld_struct(a + p), n_inv);
+    if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
+    st_struct(a + p, x);
+}
+
+// h[i] = fromMontgomery(a[i]*b[i] - c[i])   (groth16.cpp:158-163), written over a
+__global__ void __launch_bounds__(256) k_h_combine(Fr *__restrict__ a, const Fr *__restrict__ b,
+                                                   const Fr *__restrict__ c, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr t = fp_sub(fp_mul(ld_struct(a + i), ld_struct(b + i)), ld_struct(c + i));
+    st_struct(a + i, fp_from_mont(t));
+}
+
+// a[row], b[row] from the CSR-repacked coefficient records, c = a*b   (groth16.cpp:62-96).
+// wtns is in normal form and coef = value*R^2, so one Montgomery product gives Montgomery form.
+__global__ void __launch_bounds__(128) k_build_abc(const Fr *__restrict__ wtns, const u32 *__restrict__ row_ptr_a,
+                                                   const u32 *__restrict__ row_ptr_b, const u32 *__restrict__ sig,
+                                                   const Fr *__restrict__ coef, u32 n, Fr *__restrict__ a,
+                                                   Fr *__restrict__ b, Fr *__restrict__ c) {
+    u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    Fr sa = Fr::zero(), sb = Fr::zero();
+    for (u32 k = row_ptr_a[row], e = row_ptr_a[row + 1]; k < e; k++)
+        sa = fp_add(sa, fp_mul(ldg_struct(wtns + sig[k]), ldg_struct(coef + k)));
+    for (u32 k = row_ptr_b[row], e = row_ptr_b[row + 1]; k < e; k++)
+        sb = fp_add(sb, fp_mul(ldg_struct(wtns + sig[k]), ldg_struct(coef + k)));
+    st_struct(a + row, sa);
+    st_struct(b + row, sb);
+    st_struct(c + row, fp_mul(sa, sb));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static Fr host_root_of_unity(int s, bool inverse) {
+    // 5^((r-1)/2^s) (fft.cpp:52-83: nqr = 5 for BN254 r, 2-adicity 28)
+    u32 e[8];
+    for (int i = 0; i < 8; i++) e[i] = FrParams::mod(i);
+    e[0] -= 1;
+    // e >>= s
+    for (int k = 0; k < s; k++) {
+        for (int i = 0; i < 8; i++) e[i] = (e[i] >> 1) | (i < 7 ? (e[i + 1] << 31) : 0);
+    }
+    Fr five = Fr::zero();
+    five.v[0] = 5;
+    five = fp_to_mont(five);
+    Fr w = fp_pow(five, e);
+    return inverse ? fp_inv(w) : w;
+}
+
+static Fr host_pow2k(Fr w, int k) {  // w^(2^k)
+    for (int i = 0; i < k; i++) w = fp_sqr(w);
+    return w;
+}
+
+void ntt_free_tables(Ctx *ctx) {
+    if (!ctx->tw) return;
+    for (int s = 0; s < 29; s++)
+        for (int inv = 0; inv < 2; inv++) {
+            NttTable &t = ctx->tw->tab[s][inv];
+            if (t.t_lo) cudaFree(t.t_lo);
+            if (t.t_hi) cudaFree(t.t_hi);
+            if (t.loc) cudaFree(t.loc);
+        }
+    delete ctx->tw;
+    ctx->tw = nullptr;
+}
+
+static int ntt_get_table(Ctx *ctx, int k, bool inverse, NttTable *out) {
+    const int s = k + 1;   // tables of w_{2n}: also serve the coset twist
+    if (s > 28) { ctx->err = "Domain size too big for the curve"; return B200_ERR_RANGE; }
+    if (!ctx->tw) ctx->tw = new Ctx::Twiddles();
+    NttTable &t = ctx->tw->tab[s][inverse ? 1 : 0];
+    if (!t.t_lo) {
+        t.s = s;
+        t.loc_log = k < NTT_S_LAST ? (k < 1 ? 1 : k) : NTT_S_LAST;
+        Fr W = host_root_of_unity(s, inverse);
+        const u32 n_lo = 1u << NTT_LB, n_hi = s > NTT_LB ? (1u << (s - NTT_LB)) : 1u, n_loc = 1u << (t.loc_log - 1);
+        B200_CUDA_CHECK(ctx, cudaMalloc(&t.t_lo, (size_t)n_lo * sizeof(Fr)));
+        B200_CUDA_CHECK(ctx, cudaMalloc(&t.t_hi, (size_t)n_hi * sizeof(Fr)));
+        B200_CUDA_CHECK(ctx, cudaMalloc(&t.loc, (size_t)n_loc * sizeof(Fr)));
+        B200_LAUNCH(ctx, k_ntt_build_powers, (n_lo + 255) / 256, 256, 0, W, n_lo, t.t_lo);
+        B200_LAUNCH(ctx, k_ntt_build_powers, (n_hi + 255) / 256, 256, 0, host_pow2k(W, NTT_LB), n_hi, t.t_hi);
+        B200_LAUNCH(ctx, k_ntt_build_powers, (n_loc + 255) / 256, 256, 0, host_pow2k(W, s - t.loc_log), n_loc, t.loc);
+    }
+    *out = t;
+    return B200_OK;
+}
+
+struct NttPass { int lo, S, q; };
+
+static int ntt_plan(int k, NttPass *p) {   // passes ordered from the high bits down (DIF order)
+    int np = 0;
+    int last = k < NTT_S_LAST ? k : NTT_S_LAST;
+    int rest = k - last;
+    int nstr = (rest + NTT_S_STRIDED - 1) / NTT_S_STRIDED;
+    int hi = k;
+    for (int i = 0; i < nstr; i++) {
+        int S = (rest + (nstr - i) - 1) / (nstr - i);
+        rest -= S;
+        p[np].lo = hi - S;
+        p[np].S = S;
+        p[np].q = p[np].lo < NTT_Q ? p[np].lo : NTT_Q;
+        hi -= S;
+        np++;
+    }
+    p[np].lo = 0; p[np].S = last; p[np].q = 0;
+    np++;
+    return np;
+}
+
+template <bool DIT>
+static int ntt_launch_pass(Ctx *ctx, Fr *d_a, int k, const NttPass &ps, const NttTable &tb) {
+    if (ps.S == 0) return B200_OK;
+    const u32 tile_elems = 1u << (ps.S + ps.q);
+    const size_t smem = (size_t)tile_elems * 32 + (size_t)(1u << (ps.S - 1)) * 32;
+    const u32 grid = (u32)(((u64)1 << k) >> (ps.S + ps.q));
+    u32 threads = tile_elems / 2;
+    if (threads > 512) threads = 512;
+    if (threads < 32) threads = 32;
+    auto kern = k_ntt_pass<DIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    B200_LAUNCH(ctx, kern, grid, threads, smem, d_a, ps.lo, ps.S, ps.q, tb);
+    return B200_OK;
+}
+
+static int ilog2_exact(uint64_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int k = 0;
+    while ((1ull << k) < n) k++;
+    return k;
+}
+
+// natural -> bit-reversed (DIF)
+int ntt_dif(Ctx *ctx, Fr *d_a, int k, bool inverse_roots) {
+    if (k == 0) return B200_OK;
+    NttTable tb;
+    B200_TRY(ntt_get_table(ctx, k, inverse_roots, &tb));
+    NttPass p[8];
+    int np = ntt_plan(k, p);
+    for (int i = 0; i < np; i++) B200_TRY(ntt_launch_pass<false>(ctx, d_a, k, p[i], tb));
+    return B200_OK;
+}
+
+// bit-reversed -> natural (DIT)
+int ntt_dit(Ctx *ctx, Fr *d_a, int k, bool inverse_roots) {
+    if (k == 0) return B200_OK;
+    NttTable tb;
+    B200_TRY(ntt_get_table(ctx, k, inverse_roots, &tb));
+    NttPass p[8];
+    int np = ntt_plan(k, p);
+    for (int i = np - 1; i >= 0; i--) B200_TRY(ntt_launch_pass<true>(ctx, d_a, k, p[i], tb));
+    return B200_OK;
+}
+
+static Fr host_n_inv(int k) {
+    Fr two = Fr::zero();
+    two.v[0] = 2;
+    two = fp_to_mont(two);
+    Fr inv2 = fp_inv(two), r = Fr::one();
+    for (int i = 0; i < k; i++) r = fp_mul(r, inv2);
+    return r;
+}
+
+// reference-order transform: natural in, natural out (fft.cpp:175-212)
+int ntt_natural(Ctx *ctx, Fr *d_a, uint64_t n, bool inverse) {
+    int k = ilog2_exact(n);
+    if (k < 0) { ctx->err = "ntt: n must be a power of two"; return B200_ERR_ARG; }
+    if (k + 1 > 28) { ctx->err = "Domain size too big for the curve"; return B200_ERR_RANGE; }
+    if (k == 0) return B200_OK;
+    B200_LAUNCH(ctx, k_ntt_bitrev, (u32)((n + 255) / 256), 256, 0, d_a, k);
+    B200_TRY(ntt_dit(ctx, d_a, k, inverse));
+    if (inverse) B200_LAUNCH(ctx, k_ntt_scale, (u32)((n + 255) / 256), 256, 0, d_a, n, host_n_inv(k));
+    return B200_OK;
+}
+
+// a, b, c (natural order, Montgomery) -> h scalars in d_a (normal form)   (groth16.cpp:101-163)
+int h_pipeline(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n) {
+    int k = ilog2_exact(n);
+    if (k < 0) { ctx->err = "h pipeline: domain size must be a power of two"; return B200_ERR_ARG; }
+    if (k + 1 > 28) { ctx->err = "Domain size too big for the curve"; return B200_ERR_RANGE; }
+    NttTable tf;
+    B200_TRY(ntt_get_table(ctx, k, false, &tf));
+    Fr ninv = host_n_inv(k);
+    Fr *arr[3] = {d_a, d_b, d_c};
+    for (int i = 0; i < 3; i++) {
+        B200_TRY(ntt_dif(ctx, arr[i], k, true));
+        B200_LAUNCH(ctx, k_ntt_scale_twist_brev, (u32)((n + 255) / 256), 256, 0, arr[i], k, ninv, tf);
+        B200_TRY(ntt_dit(ctx, arr[i], k, false));
+    }
+    B200_LAUNCH(ctx, k_h_combine, (u32)((n + 255) / 256), 256, 0, d_a, d_b, d_c, n);
+    return B200_OK;
+}
+
+int build_abc(Ctx *ctx, const Fr *d_wtns, const u32 *d_row_a, const u32 *d_row_b, const u32 *d_sig, const Fr *d_coef,
+              u32 n, Fr *d_a, Fr *d_b, Fr *d_c) {
+    B200_LAUNCH(ctx, k_build_abc, (n + 127) / 128, 128, 0, d_wtns, d_row_a, d_row_b, d_sig, d_coef, n, d_a, d_b, d_c);
+    return B200_OK;
+}
+
+}  // namespace b200

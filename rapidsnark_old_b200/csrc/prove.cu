@@ -1,0 +1,313 @@
+// Resident zkey + the fused prove path, NTT C-ABI front ends and the fixed-base table generator.
+//
+// b200_zkey_upload mirrors Groth16::makeProver (src/groth16.cpp:9-46): it takes the raw zkey section
+// pointers, but instead of borrowing them it copies this GPU's point-range shard of every table to
+// HBM once, and repacks the 44-byte coefficient records (groth16.hpp:27-35) into CSR by (matrix, row)
+// so that the a/b build (groth16.cpp:62-85, 1024 striped locks on the CPU) is a lock-free row gather.
+// b200_prove_msms is groth16.cpp:52-207: a,b,c -> 3 x (ifft, coset twist, fft) -> h -> five MSMs.
+#include <algorithm>
+#include <vector>
+#include "ctx.cuh"
+#include "memops.cuh"
+
+namespace b200 {
+int ntt_natural(Ctx *ctx, Fr *d_a, uint64_t n, bool inverse);
+int h_pipeline(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n);
+int build_abc(Ctx *ctx, const Fr *d_wtns, const u32 *d_row_a, const u32 *d_row_b, const u32 *d_sig, const Fr *d_coef,
+              u32 n, Fr *d_a, Fr *d_b, Fr *d_c);
+}  // namespace b200
+
+using namespace b200;
+
+
+struct Range { uint64_t lo, hi; };
+
+struct b200_zkey {
+    Ctx *ctx;
+    u32 n_vars, n_public, domain_size;
+    u64 n_coefs;
+    Range rA, rC, rH;       // this shard's index ranges (A, B1, B2 share rA)
+    u32 *d_row_a = nullptr, *d_row_b = nullptr, *d_sig = nullptr;
+    Fr *d_coef = nullptr;
+    G1Affine *d_A = nullptr, *d_B1 = nullptr, *d_C = nullptr, *d_H = nullptr;
+    G2Affine *d_B2 = nullptr;
+    Fr *d_wtns = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
+};
+
+static Range shard_range(uint64_t len, u32 idx, u32 cnt) {
+    Range r;
+    r.lo = len * idx / cnt;
+    r.hi = len * (idx + 1) / cnt;
+    return r;
+}
+
+template <class T>
+static int upload_slice(Ctx *c, T **dst, const void *src, Range r) {
+    size_t cnt = (size_t)(r.hi - r.lo);
+    B200_CUDA_CHECK(c, cudaMalloc((void **)dst, std::max<size_t>(cnt, 1) * sizeof(T)));
+    if (cnt)
+        B200_CUDA_CHECK(c, cudaMemcpyAsync(*dst, (const uint8_t *)src + (size_t)r.lo * sizeof(T), cnt * sizeof(T),
+                                            cudaMemcpyHostToDevice, c->stream));
+    return B200_OK;
+}
+
+// ---- fixed-base tables (synthetic zkey generation; not on the prove path) ---------------------------
+template <class F>
+__global__ void k_fb_window_bases(Affine<F> base, Xyzz<F> *__restrict__ wb) {  // wb[w] = 2^(8w) * base
+    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 32) return;
+    Xyzz<F> p = Xyzz<F>::from_affine(base);
+    for (u32 i = 0; i < 8 * w; i++) p = ec_dbl(p);
+    st_struct(wb + w, p);
+}
+
+template <class F>
+DEVFN Affine<F> to_affine_1inv(const Xyzz<F> &p) {
+    Affine<F> r;
+    if (p.is_zero()) { r.x = F::zero(); r.y = F::zero(); return r; }
+    F i = finv(fmul(p.zz, p.zzz));
+    r.x = fmul(p.x, fmul(i, p.zzz));
+    r.y = fmul(p.y, fmul(i, p.zz));
+    return r;
+}
+
+template <class F>
+__global__ void k_fb_table(const Xyzz<F> *__restrict__ wb, Affine<F> *__restrict__ tbl) {  // tbl[w*256+d] = d * wb[w]
+    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= 32 * 256) return;
+    u32 w = g >> 8, d = g & 255;
+    Xyzz<F> p = ld_struct(wb + w);
+    Xyzz<F> r = ec_mul(p, &d, 1);
+    st_struct(tbl + g, to_affine_1inv(r));
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_fb_mul(const Affine<F> *__restrict__ tbl, const uint8_t *__restrict__ scalars,
+                                                u64 n, Affine<F> *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *s = scalars + i * 32;
+    Xyzz<F> acc = Xyzz<F>::zero();
+    for (int w = 0; w < 32; w++) {
+        u32 d = s[w];
+        if (d) {
+            Affine<F> p = ldg_struct(tbl + w * 256 + d);
+            ec_madd(acc, p);
+        }
+    }
+    st_struct(out + i, to_affine_1inv(acc));
+}
+
+template <class F>
+static int fixed_base_run(Ctx *c, const void *base_affine, const void *scalars, uint64_t n, void *out) {
+    if (!base_affine || (n && (!scalars || !out))) { c->err = "fixed_base: null argument"; return B200_ERR_ARG; }
+    if (n == 0) return B200_OK;
+    Affine<F> base;
+    memcpy(&base, base_affine, sizeof base);
+    Xyzz<F> *d_wb = nullptr;
+    Affine<F> *d_tbl = nullptr, *d_out = nullptr;
+    uint8_t *d_sc = nullptr;
+    B200_CUDA_CHECK(c, cudaMalloc(&d_wb, 32 * sizeof(Xyzz<F>)));
+    B200_CUDA_CHECK(c, cudaMalloc(&d_tbl, 32 * 256 * sizeof(Affine<F>)));
+    B200_CUDA_CHECK(c, cudaMalloc(&d_sc, n * 32));
+    B200_CUDA_CHECK(c, cudaMalloc(&d_out, n * sizeof(Affine<F>)));
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(d_sc, scalars, n * 32, cudaMemcpyHostToDevice, c->stream));
+    B200_LAUNCH(c, k_fb_window_bases<F>, 1, 32, 0, base, d_wb);
+    B200_LAUNCH(c, k_fb_table<F>, 32 * 256 / 64, 64, 0, d_wb, d_tbl);
+    B200_LAUNCH(c, k_fb_mul<F>, (u32)((n + 127) / 128), 128, 0, d_tbl, d_sc, n, d_out);
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(out, d_out, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_wb); cudaFree(d_tbl); cudaFree(d_sc); cudaFree(d_out);
+    return B200_OK;
+}
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------- NTT
+int b200_ntt_fr_dev(b200_ctx *h, void *d_a, uint64_t n, int inverse) {
+    if (!h || !d_a) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    phase_reset(c);
+    phase_begin(c, PH_NTT);
+    int rc = ntt_natural(c, (Fr *)d_a, n, inverse != 0);
+    phase_end(c);
+    if (rc != B200_OK) return rc;
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    phase_collect(c);
+    return B200_OK;
+}
+
+int b200_ntt_fr(b200_ctx *h, void *a_host, uint64_t n, int inverse) {
+    if (!h || !a_host) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    if (n == 0 || (n & (n - 1))) { c->err = "ntt: n must be a power of two"; return B200_ERR_ARG; }
+    B200_TRY(ctx_reserve(c, c->w_ntt, n * 32));
+    phase_reset(c);
+    phase_begin(c, PH_H2D);
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(c->w_ntt.p, a_host, n * 32, cudaMemcpyHostToDevice, c->stream));
+    phase_end(c);
+    phase_begin(c, PH_NTT);
+    int rc = ntt_natural(c, (Fr *)c->w_ntt.p, n, inverse != 0);
+    phase_end(c);
+    if (rc != B200_OK) return rc;
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(a_host, c->w_ntt.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    phase_collect(c);
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- zkey
+void b200_zkey_free(b200_zkey *zk) {
+    if (!zk) return;
+    cudaSetDevice(zk->ctx->device);
+    cudaStreamSynchronize(zk->ctx->stream);
+    void *all[] = {zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->d_A, zk->d_B1, zk->d_C, zk->d_H,
+                   zk->d_B2, zk->d_wtns, zk->d_a, zk->d_b, zk->d_c};
+    for (void *p : all) if (p) cudaFree(p);
+    delete zk;
+}
+
+int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
+    if (!h || !d || !out) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    if (!d->coefs || !d->points_a || !d->points_b1 || !d->points_b2 || !d->points_c || !d->points_h) {
+        c->err = "zkey_upload: null section pointer"; return B200_ERR_ARG;
+    }
+    const u32 n = d->domain_size;
+    if (n == 0 || (n & (n - 1))) { c->err = "zkey_upload: domain_size must be a power of two"; return B200_ERR_ARG; }
+    if ((uint64_t)n * 2 > (1ull << 28)) { c->err = "Domain size too big for the curve"; return B200_ERR_RANGE; }
+    if (d->n_vars == 0 || d->n_public + 1 > d->n_vars) { c->err = "zkey_upload: bad n_vars / n_public"; return B200_ERR_ARG; }
+    const u32 cnt = d->shard_count ? d->shard_count : 1;
+    if (d->shard_index >= cnt) { c->err = "zkey_upload: shard_index >= shard_count"; return B200_ERR_ARG; }
+
+    // CSR repack of section 4 (records start after the u32 count: groth16.cpp:38)
+    const uint8_t *rec = (const uint8_t *)d->coefs + 4;
+    std::vector<u32> row_a(n + 1, 0), row_b(n + 1, 0);
+    for (u64 i = 0; i < d->n_coefs; i++) {
+        u32 m, r, s;
+        memcpy(&m, rec + i * 44, 4);
+        memcpy(&r, rec + i * 44 + 4, 4);
+        memcpy(&s, rec + i * 44 + 8, 4);
+        if (m > 1 || r >= n || s >= d->n_vars) { c->err = "zkey_upload: coefficient record out of range"; return B200_ERR_ARG; }
+        (m == 0 ? row_a : row_b)[r + 1]++;
+    }
+    for (u32 r = 0; r < n; r++) row_a[r + 1] += row_a[r];
+    const u32 nnz_a = row_a[n];
+    row_b[0] = nnz_a;
+    for (u32 r = 0; r < n; r++) row_b[r + 1] += row_b[r];
+    std::vector<u32> sig(d->n_coefs ? d->n_coefs : 1);
+    std::vector<Fr> coef(d->n_coefs ? d->n_coefs : 1);
+    {
+        std::vector<u32> cur_a(row_a.begin(), row_a.end() - 1), cur_b(row_b.begin(), row_b.end() - 1);
+        for (u64 i = 0; i < d->n_coefs; i++) {
+            u32 m, r, s;
+            memcpy(&m, rec + i * 44, 4);
+            memcpy(&r, rec + i * 44 + 4, 4);
+            memcpy(&s, rec + i * 44 + 8, 4);
+            u32 k = (m == 0 ? cur_a : cur_b)[r]++;
+            sig[k] = s;
+            memcpy(&coef[k], rec + i * 44 + 12, 32);
+        }
+    }
+
+    b200_zkey *zk = new b200_zkey();
+    zk->ctx = c;
+    zk->n_vars = d->n_vars; zk->n_public = d->n_public; zk->domain_size = n; zk->n_coefs = d->n_coefs;
+    zk->rA = shard_range(d->n_vars, d->shard_index, cnt);
+    zk->rC = shard_range(d->n_vars - d->n_public - 1, d->shard_index, cnt);
+    zk->rH = shard_range(n, d->shard_index, cnt);
+    int rc = B200_OK;
+    auto fail = [&](int code) { b200_zkey_free(zk); return code; };
+#define ZK_TRY(x) do { rc = (x); if (rc != B200_OK) return fail(rc); } while (0)
+#define ZK_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { c->err = std::string("zkey_upload: ") + cudaGetErrorString(e_); return fail(B200_ERR_CUDA); } } while (0)
+    ZK_CUDA(cudaMalloc(&zk->d_row_a, (size_t)(n + 1) * 4));
+    ZK_CUDA(cudaMalloc(&zk->d_row_b, (size_t)(n + 1) * 4));
+    ZK_CUDA(cudaMalloc(&zk->d_sig, sig.size() * 4));
+    ZK_CUDA(cudaMalloc(&zk->d_coef, coef.size() * sizeof(Fr)));
+    ZK_CUDA(cudaMemcpyAsync(zk->d_row_a, row_a.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    ZK_CUDA(cudaMemcpyAsync(zk->d_row_b, row_b.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    ZK_CUDA(cudaMemcpyAsync(zk->d_sig, sig.data(), sig.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    ZK_CUDA(cudaMemcpyAsync(zk->d_coef, coef.data(), coef.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    ZK_TRY(upload_slice(c, &zk->d_A, d->points_a, zk->rA));
+    ZK_TRY(upload_slice(c, &zk->d_B1, d->points_b1, zk->rA));
+    ZK_TRY(upload_slice(c, &zk->d_B2, d->points_b2, zk->rA));
+    ZK_TRY(upload_slice(c, &zk->d_C, d->points_c, zk->rC));
+    ZK_TRY(upload_slice(c, &zk->d_H, d->points_h, zk->rH));
+    ZK_CUDA(cudaMalloc(&zk->d_wtns, (size_t)d->n_vars * sizeof(Fr)));
+    ZK_CUDA(cudaMalloc(&zk->d_a, (size_t)n * sizeof(Fr)));
+    ZK_CUDA(cudaMalloc(&zk->d_b, (size_t)n * sizeof(Fr)));
+    ZK_CUDA(cudaMalloc(&zk->d_c, (size_t)n * sizeof(Fr)));
+    ZK_CUDA(cudaStreamSynchronize(c->stream));   // host staging vectors die at return
+#undef ZK_TRY
+#undef ZK_CUDA
+    *out = zk;
+    return B200_OK;
+}
+
+static int h_on_device(Ctx *c, b200_zkey *zk, const void *wtns_host) {
+    phase_begin(c, PH_H2D);
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(zk->d_wtns, wtns_host, (size_t)zk->n_vars * 32, cudaMemcpyHostToDevice, c->stream));
+    phase_end(c);
+    phase_begin(c, PH_BUILD_AB);
+    B200_TRY(build_abc(c, zk->d_wtns, zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->domain_size, zk->d_a, zk->d_b, zk->d_c));
+    phase_end(c);
+    phase_begin(c, PH_NTT);
+    B200_TRY(h_pipeline(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size));
+    phase_end(c);
+    return B200_OK;
+}
+
+int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_out_host) {
+    if (!h || !zk || !wtns_host || !h_out_host) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    phase_reset(c);
+    B200_TRY(h_on_device(c, zk, wtns_host));
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(h_out_host, zk->d_a, (size_t)zk->domain_size * 32, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    phase_collect(c);
+    return B200_OK;
+}
+
+int b200_prove_msms(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *out768) {
+    if (!h || !zk || !wtns_host || !out768) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    cudaSetDevice(c->device);
+    phase_reset(c);
+    B200_TRY(h_on_device(c, zk, wtns_host));
+    uint8_t *o = (uint8_t *)out768;
+    G1Xyzz pih, pia, pib1, pic;
+    G2Xyzz pib;
+    const uint8_t *w = (const uint8_t *)zk->d_wtns;
+    // groth16.cpp:173 / :183 / :190 / :197 / :204, restricted to this shard's point range
+    B200_TRY(msm_g1_run(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, &pih));
+    B200_TRY(msm_g1_run(c, zk->d_A, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pia));
+    B200_TRY(msm_g1_run(c, zk->d_B1, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib1));
+    B200_TRY(msm_g2_run(c, zk->d_B2, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib));
+    B200_TRY(msm_g1_run(c, zk->d_C, w + ((size_t)zk->n_public + 1 + zk->rC.lo) * 32, 32, zk->rC.hi - zk->rC.lo, &pic));
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    phase_collect(c);
+    memcpy(o, &pih, 128);
+    memcpy(o + 128, &pia, 128);
+    memcpy(o + 256, &pib1, 128);
+    memcpy(o + 384, &pib, 256);
+    memcpy(o + 640, &pic, 128);
+    return B200_OK;
+}
+
+int b200_fixed_base_g1(b200_ctx *h, const void *base_affine64, const void *scalars32, uint64_t n, void *out_affine) {
+    if (!h) return B200_ERR_ARG;
+    cudaSetDevice(h->c.device);
+    return fixed_base_run<Fq>(&h->c, base_affine64, scalars32, n, out_affine);
+}
+int b200_fixed_base_g2(b200_ctx *h, const void *base_affine128, const void *scalars32, uint64_t n, void *out_affine) {
+    if (!h) return B200_ERR_ARG;
+    cudaSetDevice(h->c.device);
+    return fixed_base_run<Fq2>(&h->c, base_affine128, scalars32, n, out_affine);
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+"""Synthetic Groth16 zkey / wtns generator with known toxic waste.
+
+The reference ships no zkey/wtns fixtures, so every input is generated: a chain circuit
+``(w_j + 3*w_{j+1}) * w_{j+1} = w_{j+2}`` over ``n_vars = n - 6`` wires with ``n_public = 4`` public
+signals, the snarkjs-style binding rows, and all five point tables as *known* multiples of the
+generators.  Because the discrete logs are known, every MSM result of the prover can be checked as one
+scalar multiplication (``expected_*``) and a whole proof can be checked in the exponent, at any size.
+
+Layout written by ``write_zkey`` / ``write_wtns`` is exactly what the reference reads
+(src/binfile_utils.cpp:34-60, src/zkey_utils.cpp:17-52, src/wtns_utils.cpp:12-25, sections 1-9).
+
+Scalar arithmetic is Python big integers; the point tables are produced by two callables
+``g1_mul_many(list_of_ints) -> bytes`` / ``g2_mul_many`` supplied by the caller (the GPU fixed-base
+kernel ``Context.fixed_base_g1/g2`` in bench.py, the CPU oracle in the no-GPU tests).
+"""
+import random
+import struct
+
+Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+MONT = 1 << 256
+G1 = (1, 2)
+G2 = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+       11559732032986387107991004021392285783925812861821192530917403151452391805634),
+      (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+       4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+def fq_mont(x):
+    return (x * MONT % Q).to_bytes(32, "little")
+
+
+def g1_gen_bytes():
+    return fq_mont(G1[0]) + fq_mont(G1[1])
+
+
+def g2_gen_bytes():
+    return b"".join(fq_mont(v) for v in (G2[0][0], G2[0][1], G2[1][0], G2[1][1]))
+
+
+def root_of_unity(log_n):
+    w = pow(5, (R - 1) >> 28, R)
+    for _ in range(28 - log_n):
+        w = w * w % R
+    return w
+
+
+def batch_inverse(vals):
+    n = len(vals)
+    pref = [1] * (n + 1)
+    for i, v in enumerate(vals):
+        pref[i + 1] = pref[i] * v % R
+    inv = pow(pref[n], -1, R)
+    out = [0] * n
+    for i in range(n - 1, -1, -1):
+        out[i] = pref[i] * inv % R
+        inv = inv * vals[i] % R
+    return out
+
+
+def le32_many(vals):
+    return b"".join(int(v).to_bytes(32, "little") for v in vals)
+
+
+class Synth:
+    """All the pieces of one synthetic circuit instance (see module docstring)."""
+
+    def __init__(self, log_n, seed=1, n_public=4, witness="uniform"):
+        rnd = random.Random(seed)
+        n = 1 << log_n
+        assert n >= 16
+        self.log_n, self.n, self.n_public = log_n, n, n_public
+        V = self.n_vars = n - 6
+        P = n_public
+        n_cons = self.n_cons = V - 2
+        self.tau, self.alpha, self.beta, self.gamma, self.delta = (rnd.randrange(2, R) for _ in range(5))
+
+        # ---- witness (normal form).  "uniform": chain values are pseudo-random full-width field elements.
+        # "circomlike": most of the chain collapses to tiny values (w1 = 0 makes every wire 0, so instead
+        # the chain is re-seeded: blocks of zeros / ones / small values are not expressible in this
+        # circuit), so only "uniform" is a satisfiable witness; skewed scalars are exercised on the MSM
+        # level by the tests and the microbench.
+        w = [0] * V
+        w[0] = 1
+        w[1] = rnd.randrange(2, R)
+        for j in range(n_cons):
+            w[j + 2] = (w[j] + 3 * w[j + 1]) * w[j + 1] % R
+        self.wtns = w
+
+        # ---- section 4 records (m, c, s, value)
+        recs = []
+        for j in range(n_cons):
+            recs.append((0, j, j, 1))
+            recs.append((0, j, j + 1, 3))
+            recs.append((1, j, j + 1, 1))
+        for i in range(P + 1):
+            recs.append((0, n_cons + i, i, 1))
+        self.records = recs
+        self.n_coefs = len(recs)
+
+        # ---- Lagrange basis of the plain domain at tau
+        tau, omega = self.tau, root_of_unity(log_n)
+        zt = (pow(tau, n, R) - 1) % R
+        wj, dens, ws = 1, [], []
+        for j in range(n):
+            ws.append(wj)
+            dens.append(n * (tau - wj) % R)
+            wj = wj * omega % R
+        dinv = batch_inverse(dens)
+        L = [zt * ws[j] % R * dinv[j] % R for j in range(n)]
+
+        A = [0] * V
+        B = [0] * V
+        C = [0] * V
+        for (m, c, s, v) in recs:
+            if m == 0:
+                A[s] = (A[s] + v * L[c]) % R
+            else:
+                B[s] = (B[s] + v * L[c]) % R
+        for j in range(n_cons):
+            C[j + 2] = (C[j + 2] + L[j]) % R
+        self.A_tau, self.B_tau, self.C_tau = A, B, C
+        dinv_delta, ginv = pow(self.delta, -1, R), pow(self.gamma, -1, R)
+        K = [(self.beta * A[i] + self.alpha * B[i] + C[i]) % R for i in range(V)]
+        self.K = K
+        self.ic_scalars = [K[i] * ginv % R for i in range(P + 1)]
+        self.c_scalars = [K[i] * dinv_delta % R for i in range(P + 1, V)]
+
+        # ---- H table: Z(tau) * Lc_i(tau) / (-2 delta), Lagrange basis of the coset g*omega^i
+        g = root_of_unity(log_n + 1)
+        xs, x = [], g
+        for i in range(n):
+            xs.append(x)
+            x = x * omega % R
+        dens = [(-n) * (tau - xs[i]) % R for i in range(n)]
+        dinv = batch_inverse(dens)
+        tn1 = (pow(tau, n, R) + 1) % R
+        hfac = zt * pow((-2 * self.delta) % R, -1, R) % R
+        self.h_scalars_tbl = [tn1 * xs[i] % R * dinv[i] % R * hfac % R for i in range(n)]
+        self._coset = (xs, tn1, dinv)
+        self.points = None
+
+    # ---- coefficient section bytes: u32 count + 44-byte records, value stored as v*R^2 (Appendix A)
+    def coefs_section(self):
+        out = [struct.pack("<I", self.n_coefs)]
+        r2 = MONT * MONT % R
+        cache = {}
+        for (m, c, s, v) in self.records:
+            if v not in cache:
+                cache[v] = (v * r2 % R).to_bytes(32, "little")
+            out.append(struct.pack("<III", m, c, s) + cache[v])
+        return b"".join(out)
+
+    def wtns_bytes(self):
+        return le32_many(self.wtns)
+
+    def build_points(self, g1_mul_many, g2_mul_many):
+        """Fill the five tables + vk points from the known scalars."""
+        V, P = self.n_vars, self.n_public
+        self.points = {
+            "A": g1_mul_many(self.A_tau),
+            "B1": g1_mul_many(self.B_tau),
+            "B2": g2_mul_many(self.B_tau),
+            "C": g1_mul_many(self.c_scalars),
+            "H": g1_mul_many(self.h_scalars_tbl),
+            "IC": g1_mul_many(self.ic_scalars),
+        }
+        vk1 = g1_mul_many([self.alpha, self.beta, self.delta])
+        vk2 = g2_mul_many([self.beta, self.gamma, self.delta])
+        self.vk = {"alpha1": vk1[0:64], "beta1": vk1[64:128], "delta1": vk1[128:192],
+                   "beta2": vk2[0:128], "gamma2": vk2[128:256], "delta2": vk2[256:384]}
+        assert len(self.points["A"]) == 64 * V and len(self.points["C"]) == 64 * (V - P - 1)
+        return self
+
+    # ---- expected discrete logs of the five pre-blinding MSM results (groth16.cpp:165-207)
+    def expected_dlogs(self, h_scalars=None):
+        w, V, P = self.wtns, self.n_vars, self.n_public
+        ea = sum(w[i] * self.A_tau[i] for i in range(V)) % R
+        eb = sum(w[i] * self.B_tau[i] for i in range(V)) % R
+        ec = sum(w[i] * self.c_scalars[i - P - 1] for i in range(P + 1, V)) % R
+        if h_scalars is None:
+            h_scalars = self.h_evals()
+        eh = sum(h * t for h, t in zip(h_scalars, self.h_scalars_tbl)) % R
+        return {"pih": eh, "pi_a": ea, "pib1": eb, "pi_b": eb, "pi_c": ec}
+
+    def h_evals(self):
+        """(A*B - C)(x_i) on the coset, computed directly from the polynomials' values at tau-free data:
+        A(X) = sum_c a_c L_c(X) with a_c = <row c of A, w>; evaluated at x_i through the barycentric form."""
+        n, w = self.n, self.wtns
+        a = [0] * n
+        b = [0] * n
+        for (m, c, s, v) in self.records:
+            if m == 0:
+                a[c] = (a[c] + v * w[s]) % R
+            else:
+                b[c] = (b[c] + v * w[s]) % R
+        cvals = [a[i] * b[i] % R for i in range(n)]
+        omega, g = root_of_unity(self.log_n), root_of_unity(self.log_n + 1)
+        # barycentric evaluation at x = g*omega^i of the degree<n interpolant of vals on {omega^j}:
+        #   f(x) = (x^n - 1)/n * sum_j vals_j * omega^j / (x - omega^j),  x^n - 1 = -2 on the coset
+        # O(n^2): only used for small n in tests
+        assert n <= 4096, "h_evals is quadratic; use it for small domains only"
+        ws = [pow(omega, j, R) for j in range(n)]
+        out = []
+        ninv = pow(n, -1, R)
+        for i in range(n):
+            x = g * ws[i] % R
+            inv = batch_inverse([(x - ws[j]) % R for j in range(n)])
+            fa = sum(a[j] * ws[j] % R * inv[j] for j in range(n)) % R
+            fb = sum(b[j] * ws[j] % R * inv[j] for j in range(n)) % R
+            fc = sum(cvals[j] * ws[j] % R * inv[j] for j in range(n)) % R
+            k = (-2) * ninv % R
+            out.append(((fa * k) * (fb * k) - fc * k) % R)
+        return out
+
+
+# ----------------------------------------------------------------------------- iden3 binfile writers
+def _binfile(magic, version, sections):
+    out = [magic, struct.pack("<II", version, len(sections))]
+    for (typ, payload) in sections:
+        out.append(struct.pack("<IQ", typ, len(payload)))
+        out.append(payload)
+    return b"".join(out)
+
+
+def zkey_bytes(s):
+    """Sections 1-9 as the reference reads them; 10 (contributions) left empty."""
+    assert s.points is not None, "call build_points first"
+    hdr = struct.pack("<I", 32) + Q.to_bytes(32, "little") + struct.pack("<I", 32) + R.to_bytes(32, "little")
+    hdr += struct.pack("<III", s.n_vars, s.n_public, s.n)
+    hdr += s.vk["alpha1"] + s.vk["beta1"] + s.vk["beta2"] + s.vk["gamma2"] + s.vk["delta1"] + s.vk["delta2"]
+    secs = [(1, struct.pack("<I", 1)), (2, hdr), (3, s.points["IC"]), (4, s.coefs_section()),
+            (5, s.points["A"]), (6, s.points["B1"]), (7, s.points["B2"]), (8, s.points["C"]),
+            (9, s.points["H"]), (10, b"")]
+    return _binfile(b"zkey", 1, secs)
+
+
+def wtns_bytes_file(s):
+    hdr = struct.pack("<I", 32) + R.to_bytes(32, "little") + struct.pack("<I", s.n_vars)
+    return _binfile(b"wtns", 2, [(1, hdr), (2, s.wtns_bytes())])

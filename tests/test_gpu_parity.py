@@ -1,0 +1,290 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C-ABI
+(include/b200snark.h via the ctypes binding), against the CPU oracle on the same inputs, against the
+reference's own known-answer vectors, and - at sizes the oracle cannot reach in seconds - through
+size-independent properties (known discrete logs, round trips, linearity, shard folding).
+
+Bar: bit-exact.  MSM results are compared as canonical affine points (the XYZZ representative is
+free, curve.hpp:11-16); NTT / h data are compared byte for byte.
+"""
+import ctypes
+import os
+
+import pytest
+
+import bn254 as bn
+import oracle_lib
+import synth_util
+import rapidsnark_old_b200 as b200
+from rapidsnark_old_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return oracle_lib.best()
+
+
+def _g1_points(o, n, seed, zero_every=0):
+    r = bn.rng(seed)
+    g = bn.g1_aff_bytes(bn.G1_GEN)
+    pts = []
+    for i in range(n):
+        if zero_every and i % zero_every == zero_every - 1:
+            pts.append(bytes(64))
+        else:
+            pts.append(o.g1_mul_affine(g, r.randrange(1, bn.R_ORDER)))
+    return b"".join(pts)
+
+
+def _g2_points(o, n, seed, zero_every=0):
+    r = bn.rng(seed)
+    g = bn.g2_aff_bytes(bn.G2_GEN)
+    pts = []
+    for i in range(n):
+        if zero_every and i % zero_every == zero_every - 1:
+            pts.append(bytes(128))
+        else:
+            pts.append(o.g2_mul_affine(g, r.randrange(1, bn.R_ORDER)))
+    return b"".join(pts)
+
+
+def _scalars(n, seed, kind="full"):
+    r = bn.rng(seed)
+    out = []
+    for i in range(n):
+        if kind == "full":
+            v = r.getrandbits(256)                     # unreduced, like the reference's MSM bench
+        elif kind == "fr":
+            v = r.randrange(bn.R_ORDER)
+        elif kind == "skew":                           # circom-like: mostly 0/1, some small, few wide
+            u = r.random()
+            v = 0 if u < 0.35 else 1 if u < 0.7 else r.getrandbits(32) if u < 0.9 else r.randrange(bn.R_ORDER)
+        elif kind == "ones":
+            v = 1
+        elif kind == "max":
+            v = (1 << 256) - 1
+        else:
+            raise ValueError(kind)
+        out.append(bn.le32(v))
+    return b"".join(out)
+
+
+# ----------------------------------------------------------------------------- reference KATs on the GPU
+def test_multiexp2_golden_kat_gpu(ctx, orc):
+    """depends/ffiasm/c/alt_bn128_test.cpp:215-248."""
+    pts = [(1626275109576878988287730541908027724405348106427831594181487487855202143055,
+            18706364085805828895917702468512381358405767972162700276238017959231481018884),
+           (17245156998235704504461341147511350131061011207199931581281143511105381019978,
+            3858908536032228066651712470282632925312300188207189106507111128103204506804)]
+    sc = [1, 20187316456970436521602619671088988952475789765726813868033071292105413408473]
+    bases = b"".join(bn.g1_aff_bytes(P) for P in pts)
+    scalars = b"".join(bn.le32(s) for s in sc)
+    got = bn.g1_aff_from_bytes(b200.host_g1_to_affine(ctx.msm_g1(bases, scalars, 2)))
+    assert got == (9163953212624378696742080269971059027061360176019470242548968584908855004282,
+                   20922060990592511838374895951081914567856345629513259026540392951012456141360)
+
+
+def test_multiexp_algebraic_gpu(ctx, orc):
+    """alt_bn128_test.cpp:172-212 at the reference's own size: bases (i+1)G, scalars i+1, n = 40 000."""
+    n = 40000
+    g = bn.g1_aff_bytes(bn.G1_GEN)
+    bases = ctx.fixed_base_g1(g, b"".join(bn.le32(i + 1) for i in range(n)), n)
+    scalars = b"".join(bn.le32(i + 1) for i in range(n))
+    total = sum((i + 1) ** 2 for i in range(n))
+    assert b200.host_g1_to_affine(ctx.msm_g1(bases, scalars, n)) == orc.g1_mul_affine(g, total)
+
+
+# ----------------------------------------------------------------------------- MSM vs oracle
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 300, 5000, 70000])
+@pytest.mark.parametrize("kind", ["full", "skew"])
+def test_msm_g1_vs_oracle(ctx, orc, n, kind):
+    bases = _g1_points(orc, min(n, 3000), 100 + n, zero_every=7)
+    reps = (n + 2999) // 3000 if n else 0
+    bases = (bases * reps)[:64 * n] if n else b""     # repeated points: exercises P == Q inside buckets
+    scalars = _scalars(n, 200 + n, kind)
+    got = ctx.msm_g1(bases, scalars, n)
+    assert orc.g1_to_affine(got) == orc.g1_to_affine(orc.g1_msm(bases, scalars, n))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 17, 300, 4000])
+@pytest.mark.parametrize("kind", ["full", "skew"])
+def test_msm_g2_vs_oracle(ctx, orc, n, kind):
+    bases = _g2_points(orc, min(n, 500), 300 + n, zero_every=5)
+    reps = (n + 499) // 500 if n else 0
+    bases = (bases * reps)[:128 * n] if n else b""
+    scalars = _scalars(n, 400 + n, kind)
+    got = ctx.msm_g2(bases, scalars, n)
+    assert orc.g2_to_affine(got) == orc.g2_to_affine(orc.g2_msm(bases, scalars, n))
+
+
+@pytest.mark.parametrize("kind", ["ones", "max"])
+def test_msm_degenerate_scalars(ctx, orc, kind):
+    n = 2000
+    bases = _g1_points(orc, n, 7)
+    scalars = _scalars(n, 8, kind)
+    assert orc.g1_to_affine(ctx.msm_g1(bases, scalars, n)) == orc.g1_to_affine(orc.g1_msm(bases, scalars, n))
+
+
+def test_msm_all_zero_and_cancelling(ctx, orc):
+    n = 100
+    bases = _g1_points(orc, n, 9)
+    assert orc.g1_to_affine(ctx.msm_g1(bases, bytes(32 * n), n)) == bytes(64)
+    assert orc.g1_to_affine(ctx.msm_g1(bytes(64 * n), _scalars(n, 1), n)) == bytes(64)
+    # P and -P with the same scalar cancel
+    P = bases[:64]
+    negP = P[:32] + bn.to_mont((-bn.from_mont(P[32:64])) % bn.Q)
+    sc = bn.le32(123456789) * 2
+    assert orc.g1_to_affine(ctx.msm_g1(P + negP, sc, 2)) == bytes(64)
+
+
+@pytest.mark.parametrize("scalar_size", [1, 8, 16, 31])
+def test_msm_short_scalars(ctx, orc, scalar_size):
+    n = 500
+    r = bn.rng(scalar_size)
+    bases = _g1_points(orc, n, 11)
+    scalars = bytes(r.getrandbits(8) for _ in range(n * scalar_size))
+    got = ctx.msm_g1(bases, scalars, n, scalar_size)
+    assert orc.g1_to_affine(got) == orc.g1_to_affine(orc.g1_msm(bases, scalars, n, scalar_size))
+
+
+@pytest.mark.parametrize("c", [4, 7, 11, 13])
+def test_msm_window_override(ctx, orc, c):
+    n = 3000
+    bases = _g1_points(orc, n, 12)
+    scalars = _scalars(n, 13)
+    ctx.set_msm_window(c)
+    try:
+        got = ctx.msm_g1(bases, scalars, n)
+    finally:
+        ctx.set_msm_window(0)
+    assert orc.g1_to_affine(got) == orc.g1_to_affine(orc.g1_msm(bases, scalars, n))
+
+
+def test_msm_argument_errors(ctx):
+    with pytest.raises(b200.B200Error) as e:
+        ctx.msm_g1(bytes(64), bytes(64), 1, scalar_size=33)
+    assert e.value.code == b200.ERR_ARG
+
+
+# ----------------------------------------------------------------------------- MSM at full size: known dlogs
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_msm_g1_known_dlogs_full_size(ctx, orc, log_n):
+    n = 1 << log_n
+    r = bn.rng(log_n)
+    ks = [r.randrange(bn.R_ORDER) for _ in range(n)]
+    g = bn.g1_aff_bytes(bn.G1_GEN)
+    bases = ctx.fixed_base_g1(g, synth.le32_many(ks), n)
+    ss = [r.getrandbits(256) for _ in range(n)]
+    total = sum(k * s for k, s in zip(ks, ss)) % bn.R_ORDER
+    got = ctx.msm_g1(bases, synth.le32_many(ss), n)
+    assert b200.host_g1_to_affine(got) == orc.g1_mul_affine(g, total)
+
+
+def test_msm_g2_known_dlogs_2_18(ctx, orc):
+    n = 1 << 18
+    r = bn.rng(5)
+    ks = [r.randrange(bn.R_ORDER) for _ in range(n)]
+    g = bn.g2_aff_bytes(bn.G2_GEN)
+    bases = ctx.fixed_base_g2(g, synth.le32_many(ks), n)
+    ss = [r.randrange(bn.R_ORDER) for _ in range(n)]
+    total = sum(k * s for k, s in zip(ks, ss)) % bn.R_ORDER
+    got = ctx.msm_g2(bases, synth.le32_many(ss), n)
+    assert b200.host_g2_to_affine(got) == orc.g2_mul_affine(g, total)
+
+
+def test_fixed_base_vs_oracle(ctx, orc):
+    r = bn.rng(3)
+    ks = [0, 1, 2, bn.R_ORDER - 1, (1 << 256) - 1] + [r.getrandbits(256) for _ in range(40)]
+    g1, g2 = bn.g1_aff_bytes(bn.G1_GEN), bn.g2_aff_bytes(bn.G2_GEN)
+    got1 = ctx.fixed_base_g1(g1, synth.le32_many(ks), len(ks))
+    got2 = ctx.fixed_base_g2(g2, synth.le32_many(ks), len(ks))
+    for i, k in enumerate(ks):
+        assert got1[64 * i:64 * i + 64] == orc.g1_mul_affine(g1, k), i
+        assert got2[128 * i:128 * i + 128] == orc.g2_mul_affine(g2, k), i
+
+
+# ----------------------------------------------------------------------------- NTT
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 10, 11, 12, 13, 16])
+def test_ntt_vs_oracle(ctx, orc, log_n):
+    n = 1 << log_n
+    r = bn.rng(log_n)
+    data = b"".join(bn.le32(r.randrange(bn.R_ORDER)) for _ in range(n))
+    assert ctx.ntt(data) == orc.fr_fft(data)
+    assert ctx.ntt(data, inverse=True) == orc.fr_ifft(data)
+
+
+def test_ntt_reference_roundtrip_kat(ctx):
+    """alt_bn128_test.cpp:250-271: ifft(fft(x)) == x for n = 2^10, x_i = i + 1 (Montgomery)."""
+    n = 1 << 10
+    data = b"".join(bn.to_mont(i + 1, bn.R_ORDER) for i in range(n))
+    assert ctx.ntt(ctx.ntt(data), inverse=True) == data
+
+
+@pytest.mark.parametrize("log_n", [20, 22])
+def test_ntt_large_roundtrip_and_oracle(ctx, orc, log_n):
+    """three-pass plan (k > 20) and the bench size: round trip + byte equality with the oracle."""
+    import numpy as np
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    raw = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)   # < 2^254 < r: valid field elements
+    data = raw.tobytes()
+    fwd = ctx.ntt(data)
+    assert ctx.ntt(fwd, inverse=True) == data
+    if log_n <= 20:
+        assert fwd == orc.fr_fft(data)
+
+
+def test_ntt_domain_too_big(ctx):
+    with pytest.raises(b200.B200Error):
+        ctx.ntt(bytes(32 * 3))
+
+
+# ----------------------------------------------------------------------------- H pipeline + five MSMs
+def _upload(ctx, s, shard_index=0, shard_count=1):
+    p = s.points
+    return ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"],
+                           p["C"], p["H"], shard_index, shard_count)
+
+
+@pytest.mark.parametrize("log_n", [4, 6, 10, 12])
+def test_h_scalars_and_prove_msms_vs_oracle(ctx, orc, log_n):
+    s = synth_util.make(log_n)
+    coefs, wt = s.coefs_section(), s.wtns_bytes()
+    zk = _upload(ctx, s)
+    assert zk.h_scalars(wt) == orc.h_scalars(s.n, s.n_coefs, coefs, wt)
+    out = zk.prove_msms(wt)
+    p = s.points
+    ref = orc.prove_msms(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"], wt)
+    assert orc.msms_to_affine(out) == orc.msms_to_affine(ref)
+    zk.free()
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_prove_folds_to_unsharded(ctx, orc, shards):
+    """multi-GPU partition exercised on one device: shard partials fold to the full result."""
+    s = synth_util.make(10)
+    wt = s.wtns_bytes()
+    parts = []
+    for i in range(shards):
+        zk = _upload(ctx, s, i, shards)
+        parts.append(zk.prove_msms(wt))
+        zk.free()
+    folded = b200.fold_partials(parts)
+    assert orc.msms_to_affine(folded) == synth_util.expected_affine(orc, s)
+
+
+def test_zkey_upload_rejects_bad_records(ctx):
+    s = synth_util.make(4)
+    p = s.points
+    bad = bytearray(s.coefs_section())
+    bad[4 + 4:4 + 8] = (s.n + 5).to_bytes(4, "little")     # row index out of the domain
+    with pytest.raises(b200.B200Error):
+        ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, bytes(bad), p["A"], p["B1"], p["B2"], p["C"], p["H"])
