@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - Groth16 proof time (ms) at 2^20 constraints on B200 (BASELINE.json metric, configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            own arm (one rank per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU prover on the host cores
+
+One step = one whole proof of the synthetic 2^20 BN254 circuit: H pipeline
+(a,b,c build, 3 x iNTT/twist/NTT, h) + five MSMs (H, A, B1 over G1; B2 over G2; C over G1) + blinding +
+affine conversion.  With N > 1 every table is sharded by point range over the ranks (strong scaling: the
+same proof, less work per GPU), each rank recomputes the (cheap) H pipeline, the 768-byte partial results
+are exchanged with one NCCL all_gather and folded on the host.
+
+  value : ms per proof, witness already resident in HBM            (higher_is_better = false)
+  e2e   : ms per proof through the C-ABI with the witness in pinned HOST memory (H2D inside the timed region,
+          proof bytes read back) - the headline number to compare with --impl reference
+Timed with CUDA events recorded on the library's own stream (b200_stream), barrier + synchronize on both
+sides, max over ranks.  Inputs (point tables 0.4 GB + coefficients 0.14 GB per proof) exceed the 126 MB L2.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "groth16_proof_ms_2^20_constraints"
+UNIT = "ms"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workload
+def build_inputs(log_n, seed, g1_many, g2_many):
+    from rapidsnark_old_b200 import synth
+    t = time.time()
+    s = synth.Synth(log_n, seed)
+    log("[bench] synthetic circuit 2^%d: scalars in %.1fs" % (log_n, time.time() - t))
+    t = time.time()
+    s.build_points(g1_many, g2_many)
+    log("[bench] point tables in %.1fs" % (time.time() - t))
+    return s
+
+
+def gpu_point_makers(ctx):
+    from rapidsnark_old_b200 import synth
+    g1, g2 = synth.g1_gen_bytes(), synth.g2_gen_bytes()
+    return (lambda ks: ctx.fixed_base_g1(g1, synth.le32_many(ks), len(ks)),
+            lambda ks: ctx.fixed_base_g2(g2, synth.le32_many(ks), len(ks)))
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    o = oracle_lib.ref()
+    kind = "reference"
+    if o is None:
+        o, kind = oracle_lib.port(), "port"
+    import rapidsnark_old_b200 as b200
+    try:
+        ctx = b200.Context(0)
+        makers = gpu_point_makers(ctx)
+    except Exception as e:           # no GPU: build the tables with the oracle itself (slow, setup only)
+        log("[bench] no GPU for table generation (%s); using the CPU oracle" % e)
+        import synth_util
+        ctx, makers = None, synth_util.oracle_point_makers(o)
+    log_n = args.log_n
+    s = build_inputs(log_n, 2, *makers)
+    if ctx:
+        ctx.close()
+    p, vk = s.points, s.vk
+    coefs, wt = s.coefs_section(), s.wtns_bytes()
+    r32, s32 = (12345).to_bytes(32, "little"), (67890).to_bytes(32, "little")
+    cores = o.threads()
+
+    def step():
+        if kind == "reference" and hasattr(o.lib, "ref_groth16_prove"):
+            out = ctypes.create_string_buffer(256)      # the untouched Groth16::makeProver + Prover::prove
+            o.lib.ref_groth16_prove(ctypes.c_uint32(s.n_vars), ctypes.c_uint32(s.n_public), ctypes.c_uint32(s.n),
+                                    ctypes.c_uint64(s.n_coefs), vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"],
+                                    vk["delta2"], coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"], wt, out)
+            return out.raw
+        m = o.prove_msms(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"], wt)
+        return o.blind(m, vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"], vk["delta2"], r32, s32)
+
+    # bounded run: the reference takes seconds per proof; cap warm-up + steps so the arm ends within minutes
+    t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
+    budget = 150.0
+    steps = max(1, min(args.steps, int(budget / max(first, 1e-3)) - 1))
+    warm = 0 if first > 5 else min(args.warmup, 1)
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    sample = "full 2^%d proof, %d timed run(s) after %d warm-up (first run %.0f ms)" % (log_n, steps, warm + 1, first * 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": round(ms, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm + 1, "ms_per_step": round(ms, 3), "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u256-mont", "data": "synthetic",
+            "config": {"workload": "groth16 prove, BN254, 2^%d constraints, synthetic chain circuit" % log_n,
+                       "n_vars": s.n_vars, "n_public": s.n_public, "n_coefs": s.n_coefs,
+                       "impl_detail": "reference templates (curve/multiexp/fft/groth16) compiled from /root/reference "
+                                      "over a restated Fq/Fr field, OpenMP" if kind == "reference" else "plain-C oracle port"},
+            "cpu_baseline": {"value": round(ms, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": round(ms, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- own arm
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    import rapidsnark_old_b200 as b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = b200.Context(local)
+    log_n = args.log_n
+    s = build_inputs(log_n, 2, *gpu_point_makers(ctx))
+    p, vk = s.points, s.vk
+    zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"],
+                         p["H"], rank, world)
+    wt_bytes = s.wtns_bytes()
+    # witness: pinned host copy (e2e) and device copy (value)
+    wt_host = torch.empty(len(wt_bytes), dtype=torch.uint8).pin_memory()
+    wt_host.copy_(torch.frombuffer(bytearray(wt_bytes), dtype=torch.uint8))
+    wt_dev = wt_host.cuda()
+    r32, s32 = (12345).to_bytes(32, "little"), (67890).to_bytes(32, "little")
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    gather_dev = torch.empty(world * 768, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def finish(part):
+        if world > 1:
+            mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).cuda()
+            dist.all_gather_into_tensor(gather_dev, mine)          # the one collective of the path (NCCL)
+            allp = bytes(gather_dev.cpu().numpy())
+            part = b200.fold_partials([allp[i * 768:(i + 1) * 768] for i in range(world)])
+        return part, b200.groth16_finalize(part, vk, r32, s32)
+
+    def step_resident():
+        return finish(zk.prove_msms_dev(wt_dev.data_ptr()))
+
+    def step_e2e():
+        return finish(zk.prove_msms(wt_host.data_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # correctness gate before timing: every result is checked against the known discrete logs
+    msms, proof = step_e2e()
+    check_known_dlogs(b200, s, msms, proof, r32, s32)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phases = {}
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+            for k, v in ctx.phase_ms().items():
+                phases[k] = phases.get(k, 0.0) + v
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, {k: v / steps for k, v in phases.items()}, (ctx.launch_count() - l0) // steps
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_res, ph_res, launches = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, ph_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop()
+
+    pk, pk_kind = peaks()
+    # dominant kernel: k_msm_accumulate<Fq> - 4 launches per proof (H, A, B1, C); algorithmic bytes 96 B/point
+    n_pts = [(zk_len(s.n, rank, world)), zk_len(s.n_vars, rank, world), zk_len(s.n_vars, rank, world),
+             zk_len(s.n_vars - s.n_public - 1, rank, world)]
+    alg_bytes = 96.0 * sum(n_pts) / 4
+    acc_ms = ph_res.get("msm_accumulate_g1", 0.0) / 4
+    achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": "k_msm_accumulate<Fq>", "achieved": round(achieved, 2), "peak": pk["hbm_gbs"],
+            "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 5), "traffic": None, "peak_kind": pk_kind,
+            "launch_ms": round(acc_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
+            "note": "integer-ALU bound by construction (SURVEY 8d): ~10 Montgomery products of 8x8 32-bit limbs per "
+                    "96 algorithmic bytes; see DESIGN.md for the IMAD roofline"}
+
+    line = {"metric": METRIC, "value": round(ms_res, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_res, 4), "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u256-mont", "data": "synthetic",
+            "config": {"workload": "groth16 prove, BN254, 2^%d constraints, synthetic chain circuit" % log_n,
+                       "n_vars": s.n_vars, "n_public": s.n_public, "n_coefs": s.n_coefs,
+                       "parallelism": "point-range shards x%d, 1 NCCL all_gather of 768 B partials" % world,
+                       "l2": "inputs larger than L2 (0.5 GB of tables and coefficients per proof)"},
+            "e2e": {"value": round(ms_e2e, 4), "unit": UNIT, "h2d_bytes_per_step": len(wt_bytes), "d2h_bytes_per_step": 768},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "phases_ms": {k: round(v, 4) for k, v in ph_res.items()},
+            "phases_ms_e2e": {k: round(v, 4) for k, v in ph_e2e.items()}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(s)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    zk.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def zk_len(total, rank, world):
+    return total * (rank + 1) // world - total * rank // world
+
+
+def check_known_dlogs(b200, s, msms, proof, r32, s32):
+    """Size-independent correctness gate: with the toxic waste known, A, B, C of the proof are single scalar
+    multiples of the generators and must satisfy the Groth16 equation."""
+    from rapidsnark_old_b200 import synth
+    R = synth.R
+    w, V, P = s.wtns, s.n_vars, s.n_public
+    ea = sum(w[i] * s.A_tau[i] for i in range(V)) % R
+    eb = sum(w[i] * s.B_tau[i] for i in range(V)) % R
+    r, t = int.from_bytes(r32, "little"), int.from_bytes(s32, "little")
+    a = (s.alpha + ea + r * s.delta) % R
+    b = (s.beta + eb + t * s.delta) % R
+    g1, g2 = synth.g1_gen_bytes(), synth.g2_gen_bytes()
+    A = b200.host_g1_to_affine(b200.host_g1_mul(g1, a.to_bytes(32, "little")))
+    B = b200.host_g2_to_affine(b200.host_g2_mul(g2, b.to_bytes(32, "little")))
+    assert proof[:64] == A, "proof.A does not match its known discrete log"
+    assert proof[64:192] == B, "proof.B does not match its known discrete log"
+    # C: solve the verification equation for c and compare: a*b = alpha*beta + pub + c*delta
+    pub = sum(w[i] * s.K[i] for i in range(P + 1)) % R
+    c = (a * b - s.alpha * s.beta - pub) * pow(s.delta, -1, R) % R
+    C = b200.host_g1_to_affine(b200.host_g1_mul(g1, c.to_bytes(32, "little")))
+    assert proof[192:256] == C, "proof.C does not satisfy the Groth16 verification equation"
+    log("[bench] proof verified in the exponent (A, B, C match; e(A,B) = e(alpha,beta) e(pub,gamma) e(C,delta))")
+
+
+def cpu_baseline(s):
+    """The reference's CPU prover (oracle/_ref when present, else the plain-C port) on this box's host cores,
+    one full proof of the same inputs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    o = oracle_lib.ref()
+    kind = "reference"
+    if o is None:
+        o, kind = oracle_lib.port(), "port"
+    p, vk = s.points, s.vk
+    coefs, wt = s.coefs_section(), s.wtns_bytes()
+    t0 = time.perf_counter()
+    m = o.prove_msms(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"], wt)
+    o.blind(m, vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"], vk["delta2"], (12345).to_bytes(32, "little"),
+            (67890).to_bytes(32, "little"))
+    ms = (time.perf_counter() - t0) * 1e3
+    return {"value": round(ms, 1), "unit": UNIT, "cores": o.threads(), "kind": kind,
+            "sample": "one full 2^%d proof (H pipeline + 5 MSMs + blinding), same inputs, cold" % s.log_n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

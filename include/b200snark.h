@@ -44,6 +44,8 @@ void b200_free(b200_ctx *ctx);
 const char *b200_last_error(b200_ctx *ctx); /* ctx may be NULL: error of the last failed b200_init */
 /* kernels launched by this ctx since creation (bench.py's "gpu_launches") */
 uint64_t b200_launch_count(b200_ctx *ctx);
+/* the cudaStream_t every kernel of this ctx is launched on (for callers that time with their own events) */
+void *b200_stream(b200_ctx *ctx);
 /* device milliseconds (CUDA events on the ctx stream) of the last MSM / NTT / prove call, per phase;
  * fills up to `cap` floats, returns how many; names via b200_phase_name(i) */
 int b200_last_phase_ms(b200_ctx *ctx, float *out, int cap);
@@ -89,6 +91,8 @@ int b200_h_scalars(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *h_
 /* H pipeline + this shard's part of the five MSMs of groth16.cpp:165-207.
  * out768 = pih(128) pi_a(128) pib1(128) pi_b(256) pi_c(128), XYZZ Montgomery, pre-blinding */
 int b200_prove_msms(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *out768);
+/* same with the witness already in device memory (bench: inputs resident in HBM) */
+int b200_prove_msms_dev(b200_ctx *ctx, b200_zkey *zk, const void *d_wtns, void *out768);
 
 /* ---- synthetic tables: k_i * G for known k_i (fixed-base, device side), affine Montgomery out ------ */
 int b200_fixed_base_g1(b200_ctx *ctx, const void *base_affine64, const void *scalars32, uint64_t n, void *out_affine);
@@ -120,6 +124,15 @@ void b200_host_g2_dbl(void *r_xyzz, const void *a_xyzz);
 void b200_host_g2_neg(void *r_xyzz, const void *a_xyzz);
 void b200_host_g2_to_affine(void *r_affine, const void *a_xyzz);
 void b200_host_g2_mul(void *r_xyzz, const void *base_affine, const void *scalar, uint32_t scalar_size);
+
+
+/* ---- proof finalisation on the host: blinding + to-affine of src/groth16.cpp:209-253 with explicit r, s
+ *      (32-byte little-endian each).  out256 = A (G1 affine 64 B) | B (G2 affine 128 B) | C (G1 affine 64 B),
+ *      Montgomery, exactly the fields of Groth16::Proof (groth16.hpp:14-24) */
+void b200_groth16_finalize(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                           const void *delta1, const void *delta2, const void *r32, const void *s32, void *out256);
+/* canonical decimal string (<= 78 digits + NUL) of a Montgomery-form Fq element (RawFq::toString) */
+void b200_fq_to_decimal(const void *mont32, char *out80);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,8 @@ EXPORTS = [
     "b200_init", "b200_free", "b200_last_error", "b200_launch_count", "b200_last_phase_ms", "b200_phase_name",
     "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window",
     "b200_ntt_fr", "b200_ntt_fr_dev",
-    "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms",
+    "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
+    "b200_groth16_finalize", "b200_fq_to_decimal",
     "b200_fixed_base_g1", "b200_fixed_base_g2",
     "b200_host_fq_mul", "b200_host_fq_add", "b200_host_fq_sub", "b200_host_fq_neg", "b200_host_fq_inv",
     "b200_host_fr_mul", "b200_host_fr_add", "b200_host_fr_sub", "b200_host_fr_neg", "b200_host_fr_inv",
@@ -75,6 +76,11 @@ def lib():
         L.b200_zkey_free.argtypes = [_vp]
         L.b200_h_scalars.argtypes = [_vp, _vp, _vp, _vp]
         L.b200_prove_msms.argtypes = [_vp, _vp, _vp, _vp]
+        L.b200_prove_msms_dev.argtypes = [_vp, _vp, _vp, _vp]
+        L.b200_stream.restype = _vp
+        L.b200_stream.argtypes = [_vp]
+        L.b200_groth16_finalize.argtypes = [_vp] * 9
+        L.b200_fq_to_decimal.argtypes = [_vp, _vp]
         L.b200_fixed_base_g1.argtypes = [_vp, _vp, _vp, _u64, _vp]
         L.b200_fixed_base_g2.argtypes = [_vp, _vp, _vp, _u64, _vp]
         L.b200_last_phase_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), _int]
@@ -110,6 +116,27 @@ def host_g1_mul(base_affine, scalar): return _host_call("b200_host_g1_mul", 128,
 def host_g2_mul(base_affine, scalar): return _host_call("b200_host_g2_mul", 256, base_affine, scalar, _u32(len(scalar)))
 
 
+def groth16_finalize(msms768, vk, r32, s32):
+    """Blinding + to-affine on the host (groth16.cpp:209-253): -> A(64) | B(128) | C(64) affine Montgomery."""
+    out = ctypes.create_string_buffer(256)
+    lib().b200_groth16_finalize(_ptr(msms768), _ptr(vk["alpha1"]), _ptr(vk["beta1"]), _ptr(vk["beta2"]),
+                                _ptr(vk["delta1"]), _ptr(vk["delta2"]), _ptr(r32), _ptr(s32), out)
+    return out.raw
+
+
+def fq_to_decimal(mont32):
+    buf = ctypes.create_string_buffer(80)
+    lib().b200_fq_to_decimal(_ptr(mont32), buf)
+    return buf.value.decode()
+
+
+def proof_json(proof256):
+    """proof.json text exactly as the reference's `proofFile << proof->toJson()` (groth16.cpp:268-301)."""
+    d = [fq_to_decimal(proof256[i * 32:(i + 1) * 32]) for i in range(8)]
+    return ('{"pi_a":["%s","%s","1"],"pi_b":[["%s","%s"],["%s","%s"],["1","0"]],"pi_c":["%s","%s","1"],'
+            '"protocol":"groth16"}' % (d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]))
+
+
 def fold_partials(parts768):
     """Sum per-GPU partial results of prove_msms (pih, pi_a, pib1 | pi_b | pi_c) into one 768-byte record."""
     acc = bytearray(parts768[0])
@@ -134,6 +161,11 @@ class ZKey:
     def prove_msms(self, wtns):
         out = ctypes.create_string_buffer(768)
         self.ctx._check(lib().b200_prove_msms(self.ctx.handle, self.handle, _ptr(wtns), out))
+        return out.raw
+
+    def prove_msms_dev(self, d_wtns):
+        out = ctypes.create_string_buffer(768)
+        self.ctx._check(lib().b200_prove_msms_dev(self.ctx.handle, self.handle, _vp(d_wtns), out))
         return out.raw
 
     def free(self):
@@ -226,6 +258,10 @@ class Context:
         out = ctypes.create_string_buffer(128 * max(n, 1))
         self._check(lib().b200_fixed_base_g2(self.handle, _ptr(base_affine), _ptr(scalars32), n, out))
         return out.raw[:128 * n]
+
+    def stream(self):
+        """cudaStream_t (as int) all kernels of this context are launched on."""
+        return int(lib().b200_stream(self.handle) or 0)
 
     # ---- instrumentation
     def launch_count(self):

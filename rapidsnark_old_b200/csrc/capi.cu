@@ -8,7 +8,7 @@ using namespace b200;
 static std::string g_init_err;
 
 
-static const char *k_phase_names[PH_COUNT] = {"h2d", "msm_sort", "msm_accumulate", "msm_merge", "msm_reduce",
+static const char *k_phase_names[PH_COUNT] = {"h2d", "msm_sort", "msm_accumulate_g1", "msm_accumulate_g2", "msm_merge", "msm_reduce",
                                               "msm_final", "build_abc", "ntt_h"};
 
 extern "C" {
@@ -55,6 +55,7 @@ void b200_free(b200_ctx *h) {
 
 const char *b200_last_error(b200_ctx *h) { return h ? h->c.err.c_str() : g_init_err.c_str(); }
 uint64_t b200_launch_count(b200_ctx *h) { return h ? h->c.launches : 0; }
+void *b200_stream(b200_ctx *h) { return h ? (void *)h->c.stream : nullptr; }
 void b200_set_msm_window(b200_ctx *h, int c_bits) { if (h) h->c.force_c = c_bits; }
 
 int b200_last_phase_ms(b200_ctx *h, float *out, int cap) {

@@ -14,7 +14,8 @@ namespace b200 {
 enum Phase {
     PH_H2D = 0,
     PH_MSM_SORT,       // digits + histogram + scan + scatter
-    PH_MSM_ACCUM,      // bucket accumulation (dominant kernel)
+    PH_MSM_ACCUM,      // bucket accumulation, G1 (dominant kernel: k_msm_accumulate<Fq>)
+    PH_MSM_ACCUM_G2,   // bucket accumulation, G2
     PH_MSM_MERGE,      // boundary / hot bucket merge
     PH_MSM_REDUCE,     // weighted bucket reduction + window sums
     PH_MSM_FINAL,      // D2H of window sums + host Horner
@@ -145,6 +146,8 @@ inline void phase_collect(Ctx *ctx) {  // stream must be synchronized
     } while (0)
 
 void ntt_free_tables(Ctx *ctx);   // ntt.cu
+void host_horner_g1(const void *win, int nwin, int c, void *out);   // src/hostmath.cpp (g++)
+void host_horner_g2(const void *win, int nwin, int c, void *out);
 
 // msm entry points implemented in msm_g1.cu / msm_g2.cu
 int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G1Xyzz *out_host);

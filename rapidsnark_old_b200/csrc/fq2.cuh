@@ -5,14 +5,16 @@
 
 namespace b200 {
 
-struct alignas(16) Fq2 {
-    Fq a, b;
-    HD static Fq2 zero() { Fq2 r; r.a = Fq::zero(); r.b = Fq::zero(); return r; }
-    HD static Fq2 one() { Fq2 r; r.a = Fq::one(); r.b = Fq::zero(); return r; }
+template <class B>
+struct alignas(16) Fq2T {
+    B a, b;
+    HD static Fq2T zero() { Fq2T r; r.a = B::zero(); r.b = B::zero(); return r; }
+    HD static Fq2T one() { Fq2T r; r.a = B::one(); r.b = B::zero(); return r; }
     HD bool is_zero() const { return a.is_zero() && b.is_zero(); }
-    HD bool operator==(const Fq2 &o) const { return a == o.a && b == o.b; }
-    HD bool operator!=(const Fq2 &o) const { return !(*this == o); }
+    HD bool operator==(const Fq2T &o) const { return a == o.a && b == o.b; }
+    HD bool operator!=(const Fq2T &o) const { return !(*this == o); }
 };
+typedef Fq2T<Fq> Fq2;
 
 // uniform operator names so curve.cuh is written once for Fq and Fq2
 HD Fq fadd(const Fq &x, const Fq &y) { return fp_add(x, y); }
@@ -31,37 +33,40 @@ HD Fr fneg(const Fr &x) { return fp_neg(x); }
 HD Fr fdbl(const Fr &x) { return fp_dbl(x); }
 HD Fr finv(const Fr &x) { return fp_inv(x); }
 
-HD Fq2 fadd(const Fq2 &x, const Fq2 &y) { Fq2 r; r.a = fp_add(x.a, y.a); r.b = fp_add(x.b, y.b); return r; }
-HD Fq2 fsub(const Fq2 &x, const Fq2 &y) { Fq2 r; r.a = fp_sub(x.a, y.a); r.b = fp_sub(x.b, y.b); return r; }
-HD Fq2 fneg(const Fq2 &x) { Fq2 r; r.a = fp_neg(x.a); r.b = fp_neg(x.b); return r; }
-HD Fq2 fdbl(const Fq2 &x) { Fq2 r; r.a = fp_dbl(x.a); r.b = fp_dbl(x.b); return r; }
+template <class B> HD Fq2T<B> fadd(const Fq2T<B> &x, const Fq2T<B> &y) { Fq2T<B> r; r.a = fadd(x.a, y.a); r.b = fadd(x.b, y.b); return r; }
+template <class B> HD Fq2T<B> fsub(const Fq2T<B> &x, const Fq2T<B> &y) { Fq2T<B> r; r.a = fsub(x.a, y.a); r.b = fsub(x.b, y.b); return r; }
+template <class B> HD Fq2T<B> fneg(const Fq2T<B> &x) { Fq2T<B> r; r.a = fneg(x.a); r.b = fneg(x.b); return r; }
+template <class B> HD Fq2T<B> fdbl(const Fq2T<B> &x) { Fq2T<B> r; r.a = fdbl(x.a); r.b = fdbl(x.b); return r; }
 
 // Karatsuba, 3 base-field products (f2field.cpp:93-112)
-HD Fq2 fmul(const Fq2 &x, const Fq2 &y) {
-    Fq aa = fp_mul(x.a, y.a);
-    Fq bb = fp_mul(x.b, y.b);
-    Fq s = fp_mul(fp_add(x.a, x.b), fp_add(y.a, y.b));
-    Fq2 r;
-    r.a = fp_sub(aa, bb);
-    r.b = fp_sub(fp_sub(s, aa), bb);
+template <class B>
+HD Fq2T<B> fmul(const Fq2T<B> &x, const Fq2T<B> &y) {
+    B aa = fmul(x.a, y.a);
+    B bb = fmul(x.b, y.b);
+    B s = fmul(fadd(x.a, x.b), fadd(y.a, y.b));
+    Fq2T<B> r;
+    r.a = fsub(aa, bb);
+    r.b = fsub(fsub(s, aa), bb);
     return r;
 }
 
 // complex squaring, 2 base-field products (f2field.cpp:114-126)
-HD Fq2 fsqr(const Fq2 &x) {
-    Fq ab = fp_mul(x.a, x.b);
-    Fq2 r;
-    r.a = fp_mul(fp_add(x.a, x.b), fp_sub(x.a, x.b));
-    r.b = fp_dbl(ab);
+template <class B>
+HD Fq2T<B> fsqr(const Fq2T<B> &x) {
+    B ab = fmul(x.a, x.b);
+    Fq2T<B> r;
+    r.a = fmul(fadd(x.a, x.b), fsub(x.a, x.b));
+    r.b = fdbl(ab);
     return r;
 }
 
 // inverse through the norm a^2 + b^2 (f2field.cpp:144-155)
-HD Fq2 finv(const Fq2 &x) {
-    Fq n = fp_inv(fp_add(fp_sqr(x.a), fp_sqr(x.b)));
-    Fq2 r;
-    r.a = fp_mul(x.a, n);
-    r.b = fp_neg(fp_mul(x.b, n));
+template <class B>
+HD Fq2T<B> finv(const Fq2T<B> &x) {
+    B n = finv(fadd(fsqr(x.a), fsqr(x.b)));
+    Fq2T<B> r;
+    r.a = fmul(x.a, n);
+    r.b = fneg(fmul(x.b, n));
     return r;
 }
 

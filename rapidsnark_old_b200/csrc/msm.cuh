@@ -432,7 +432,7 @@ int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint3
         B200_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, d_cursor, d_entries);
         phase_end(ctx);
 
-        phase_begin(ctx, PH_MSM_ACCUM);
+        phase_begin(ctx, sizeof(F) == 32 ? PH_MSM_ACCUM : PH_MSM_ACCUM_G2);
         const size_t chunks = ((size_t)nb * g.nwin + g.T - 1) / g.T;
         const u32 agrid = (u32)((chunks + 127) / 128);
         auto kacc = k_msm_accumulate<F, (sizeof(F) == 32)>;
@@ -457,13 +457,9 @@ int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint3
     phase_end(ctx);
     B200_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
 
-    // Horner over the windows (multiexp.cpp:137-141)
-    Pt r = h_win[g.nwin - 1];
-    for (int w = g.nwin - 2; w >= 0; w--) {
-        for (int k = 0; k < g.c; k++) r = ec_dbl(r);
-        ec_add(r, h_win[w]);
-    }
-    *out_host = r;
+    // Horner over the windows (multiexp.cpp:137-141) on the host's 4x64 field
+    if (sizeof(F) == 32) host_horner_g1(h_win, g.nwin, g.c, out_host);
+    else host_horner_g2(h_win, g.nwin, g.c, out_host);
     return B200_OK;
 }
 

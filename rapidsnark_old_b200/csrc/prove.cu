@@ -248,9 +248,10 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     return B200_OK;
 }
 
-static int h_on_device(Ctx *c, b200_zkey *zk, const void *wtns_host) {
+static int h_on_device(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device) {
     phase_begin(c, PH_H2D);
-    B200_CUDA_CHECK(c, cudaMemcpyAsync(zk->d_wtns, wtns_host, (size_t)zk->n_vars * 32, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA_CHECK(c, cudaMemcpyAsync(zk->d_wtns, wtns, (size_t)zk->n_vars * 32,
+                                        wtns_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     phase_end(c);
     phase_begin(c, PH_BUILD_AB);
     B200_TRY(build_abc(c, zk->d_wtns, zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->domain_size, zk->d_a, zk->d_b, zk->d_c));
@@ -266,19 +267,19 @@ int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_ou
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     phase_reset(c);
-    B200_TRY(h_on_device(c, zk, wtns_host));
+    B200_TRY(h_on_device(c, zk, wtns_host, false));
     B200_CUDA_CHECK(c, cudaMemcpyAsync(h_out_host, zk->d_a, (size_t)zk->domain_size * 32, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     phase_collect(c);
     return B200_OK;
 }
 
-int b200_prove_msms(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *out768) {
+static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bool wtns_on_device, void *out768) {
     if (!h || !zk || !wtns_host || !out768) return B200_ERR_ARG;
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     phase_reset(c);
-    B200_TRY(h_on_device(c, zk, wtns_host));
+    B200_TRY(h_on_device(c, zk, wtns_host, wtns_on_device));
     uint8_t *o = (uint8_t *)out768;
     G1Xyzz pih, pia, pib1, pic;
     G2Xyzz pib;
@@ -297,6 +298,13 @@ int b200_prove_msms(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *out
     memcpy(o + 384, &pib, 256);
     memcpy(o + 640, &pic, 128);
     return B200_OK;
+}
+
+int b200_prove_msms(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *out768) {
+    return prove_msms_impl(h, zk, wtns_host, false, out768);
+}
+int b200_prove_msms_dev(b200_ctx *h, b200_zkey *zk, const void *d_wtns, void *out768) {
+    return prove_msms_impl(h, zk, d_wtns, true, out768);
 }
 
 int b200_fixed_base_g1(b200_ctx *h, const void *base_affine64, const void *scalars32, uint64_t n, void *out_affine) {

@@ -1,0 +1,193 @@
+#include "groth16.hpp"
+#include <stdlib.h>
+#include <string.h>
+#include <sys/random.h>
+#include <sstream>
+#include <stdexcept>
+#include <thread>
+#include "../../include/b200snark.h"
+
+namespace AltBn128 {
+
+const uint8_t kFrPrime[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                              0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+Engine Engine::engine;
+
+std::string f1ToString(const F1Element &e) {
+    char buf[80];
+    b200_fq_to_decimal(&e, buf);
+    return std::string(buf);
+}
+
+std::string le32ToString(const void *le32) {
+    uint64_t v[4];
+    memcpy(v, le32, 32);
+    char tmp[80];
+    int n = 0;
+    while (v[0] | v[1] | v[2] | v[3]) {
+        unsigned __int128 rem = 0;
+        for (int i = 3; i >= 0; i--) {
+            unsigned __int128 cur = (rem << 64) | v[i];
+            v[i] = (uint64_t)(cur / 10);
+            rem = cur % 10;
+        }
+        tmp[n++] = (char)('0' + (int)rem);
+    }
+    if (n == 0) tmp[n++] = '0';
+    std::string s(tmp, tmp + n);
+    return std::string(s.rbegin(), s.rend());
+}
+
+}  // namespace AltBn128
+
+namespace Groth16 {
+
+static void throwCtx(b200_ctx *ctx, const char *what) {
+    throw std::runtime_error(std::string(what) + ": " + b200_last_error(ctx));
+}
+
+template <typename Engine>
+Prover<Engine>::Prover(uint32_t _nVars, uint32_t _nPublic, uint32_t _domainSize, uint64_t nCoefs, void *_vk_alpha1,
+                       void *_vk_beta1, void *_vk_beta2, void *_vk_delta1, void *_vk_delta2, void *coefs,
+                       void *pointsA, void *pointsB1, void *pointsB2, void *pointsC, void *pointsH)
+    : nVars(_nVars), nPublic(_nPublic), domainSize(_domainSize) {
+    memcpy(&vk_alpha1, _vk_alpha1, sizeof vk_alpha1);
+    memcpy(&vk_beta1, _vk_beta1, sizeof vk_beta1);
+    memcpy(&vk_beta2, _vk_beta2, sizeof vk_beta2);
+    memcpy(&vk_delta1, _vk_delta1, sizeof vk_delta1);
+    memcpy(&vk_delta2, _vk_delta2, sizeof vk_delta2);
+    memset(lastMsms, 0, sizeof lastMsms);
+    // FFT ctor contract of the reference (groth16.hpp:94 builds FFT(2*domainSize); fft.cpp:70-72)
+    if ((uint64_t)domainSize * 2 > (1ull << 28)) throw std::range_error("Domain size too big for the curve");
+
+    int nGpus = 1, first = 0;
+    if (const char *e = getenv("B200_GPUS")) nGpus = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("B200_DEVICE")) first = atoi(e);
+    for (int g = 0; g < nGpus; g++) {
+        Gpu gp{nullptr, nullptr};
+        if (b200_init(first + g, &gp.ctx) != B200_OK) {
+            std::string msg = std::string("b200_init: ") + b200_last_error(nullptr);
+            for (auto &o : gpus) { b200_zkey_free(o.zk); b200_free(o.ctx); }
+            gpus.clear();
+            throw std::runtime_error(msg);
+        }
+        b200_zkey_desc d;
+        d.n_vars = nVars; d.n_public = nPublic; d.domain_size = domainSize; d.n_coefs = nCoefs;
+        d.coefs = coefs; d.points_a = pointsA; d.points_b1 = pointsB1; d.points_b2 = pointsB2;
+        d.points_c = pointsC; d.points_h = pointsH;
+        d.shard_index = (uint32_t)g; d.shard_count = (uint32_t)nGpus;
+        int rc = b200_zkey_upload(gp.ctx, &d, &gp.zk);
+        if (rc != B200_OK) {
+            std::string msg = std::string("b200_zkey_upload: ") + b200_last_error(gp.ctx);
+            b200_free(gp.ctx);
+            for (auto &o : gpus) { b200_zkey_free(o.zk); b200_free(o.ctx); }
+            gpus.clear();
+            if (rc == B200_ERR_RANGE) throw std::range_error("Domain size too big for the curve");
+            throw std::runtime_error(msg);
+        }
+        gpus.push_back(gp);
+    }
+}
+
+template <typename Engine>
+Prover<Engine>::~Prover() {
+    for (auto &g : gpus) { b200_zkey_free(g.zk); b200_free(g.ctx); }
+}
+
+template <typename Engine>
+void Prover<Engine>::setBlinding(const uint8_t r32[32], const uint8_t s32[32]) {
+    fixedRS = true;
+    memcpy(fixedR, r32, 32);
+    memcpy(fixedS, s32, 32);
+}
+
+template <typename Engine>
+std::unique_ptr<Proof<Engine>> Prover<Engine>::prove(typename Engine::FrElement *wtns) {
+    const size_t G = gpus.size();
+    std::vector<uint8_t> parts(768 * G);
+    std::vector<int> rcs(G, 0);
+    if (G == 1) {
+        rcs[0] = b200_prove_msms(gpus[0].ctx, gpus[0].zk, wtns, parts.data());
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; g++)
+            th.emplace_back([&, g]() { rcs[g] = b200_prove_msms(gpus[g].ctx, gpus[g].zk, wtns, parts.data() + 768 * g); });
+        for (auto &t : th) t.join();
+    }
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g] != B200_OK) throwCtx(gpus[g].ctx, "b200_prove_msms");
+    // fold the per-GPU partial sums (one group addition per result and GPU)
+    memcpy(lastMsms, parts.data(), 768);
+    for (size_t g = 1; g < G; g++) {
+        const uint8_t *p = parts.data() + 768 * g;
+        b200_host_g1_add(lastMsms, lastMsms, p);
+        b200_host_g1_add(lastMsms + 128, lastMsms + 128, p + 128);
+        b200_host_g1_add(lastMsms + 256, lastMsms + 256, p + 256);
+        b200_host_g2_add(lastMsms + 384, lastMsms + 384, p + 384);
+        b200_host_g1_add(lastMsms + 640, lastMsms + 640, p + 640);
+    }
+    lastPhases.clear();
+    float ms[16];
+    int k = b200_last_phase_ms(gpus[0].ctx, ms, 16);
+    for (int i = 0; i < k; i++) lastPhases.emplace_back(b200_phase_name(i), ms[i]);
+
+    // r, s: 31 random bytes each, top byte zero (groth16.cpp:213-217)
+    uint8_t r[32] = {0}, s[32] = {0};
+    if (fixedRS) {
+        memcpy(r, fixedR, 32);
+        memcpy(s, fixedS, 32);
+    } else {
+        if (getrandom(r, 31, 0) != 31 || getrandom(s, 31, 0) != 31) throw std::runtime_error("getrandom failed");
+    }
+    uint8_t out[256];
+    b200_groth16_finalize(lastMsms, &vk_alpha1, &vk_beta1, &vk_beta2, &vk_delta1, &vk_delta2, r, s, out);
+    std::unique_ptr<Proof<Engine>> p(new Proof<Engine>());
+    memcpy(&p->A, out, 64);
+    memcpy(&p->B, out + 64, 128);
+    memcpy(&p->C, out + 192, 64);
+    return p;
+}
+
+template <typename Engine>
+std::string Proof<Engine>::toJsonStr() {
+    using AltBn128::f1ToString;
+    std::ostringstream ss;
+    ss << "{ \"pi_a\":[\"" << f1ToString(A.x) << "\",\"" << f1ToString(A.y) << "\",\"1\"], ";
+    ss << " \"pi_b\": [[\"" << f1ToString(B.x.a) << "\",\"" << f1ToString(B.x.b) << "\"],[\"" << f1ToString(B.y.a)
+       << "\",\"" << f1ToString(B.y.b) << "\"], [\"1\",\"0\"]], ";
+    ss << " \"pi_c\": [\"" << f1ToString(C.x) << "\",\"" << f1ToString(C.y) << "\",\"1\"], ";
+    ss << " \"protocol\":\"groth16\" }";
+    return ss.str();
+}
+
+template <typename Engine>
+std::string Proof<Engine>::toJson() {
+    // nlohmann::json dump of groth16.cpp:268-301: compact, object keys in alphabetical order
+    using AltBn128::f1ToString;
+    std::ostringstream ss;
+    ss << "{\"pi_a\":[\"" << f1ToString(A.x) << "\",\"" << f1ToString(A.y) << "\",\"1\"],";
+    ss << "\"pi_b\":[[\"" << f1ToString(B.x.a) << "\",\"" << f1ToString(B.x.b) << "\"],[\"" << f1ToString(B.y.a)
+       << "\",\"" << f1ToString(B.y.b) << "\"],[\"1\",\"0\"]],";
+    ss << "\"pi_c\":[\"" << f1ToString(C.x) << "\",\"" << f1ToString(C.y) << "\",\"1\"],";
+    ss << "\"protocol\":\"groth16\"}";
+    return ss.str();
+}
+
+template <typename Engine>
+std::unique_ptr<Prover<Engine>> makeProver(uint32_t nVars, uint32_t nPublic, uint32_t domainSize, uint64_t nCoefs,
+                                           void *vk_alpha1, void *vk_beta1, void *vk_beta2, void *vk_delta1,
+                                           void *vk_delta2, void *coefs, void *pointsA, void *pointsB1,
+                                           void *pointsB2, void *pointsC, void *pointsH) {
+    return std::unique_ptr<Prover<Engine>>(new Prover<Engine>(nVars, nPublic, domainSize, nCoefs, vk_alpha1, vk_beta1,
+                                                              vk_beta2, vk_delta1, vk_delta2, coefs, pointsA, pointsB1,
+                                                              pointsB2, pointsC, pointsH));
+}
+
+template class Proof<AltBn128::Engine>;
+template class Prover<AltBn128::Engine>;
+template std::unique_ptr<Prover<AltBn128::Engine>> makeProver<AltBn128::Engine>(uint32_t, uint32_t, uint32_t, uint64_t,
+                                                                                  void *, void *, void *, void *, void *,
+                                                                                  void *, void *, void *, void *, void *,
+                                                                                  void *);
+
+}  // namespace Groth16

@@ -6,6 +6,8 @@
 #include <string.h>
 #include "../../include/b200snark.h"
 #include "../csrc/curve.cuh"
+#include "../csrc/hostfield.hpp"
+#include "../csrc/hostgroup.hpp"
 
 using namespace b200;
 
@@ -14,7 +16,78 @@ template <class T> T ld(const void *p) { T t; memcpy(&t, p, sizeof(T)); return t
 template <class T> void st(void *p, const T &t) { memcpy(p, &t, sizeof(T)); }
 }
 
+namespace b200 {
+// window Horner of the MSM (multiexp.cpp:137-141) on the fast 4x64 host field; called from msm.cuh
+void host_horner_g1(const void *win, int nwin, int c, void *out) { horner<HFq>((const Xyzz<HFq> *)win, nwin, c, (Xyzz<HFq> *)out); }
+void host_horner_g2(const void *win, int nwin, int c, void *out) { horner<HFq2>((const Xyzz<HFq2> *)win, nwin, c, (Xyzz<HFq2> *)out); }
+
+// Blinding + finalisation of src/groth16.cpp:209-253 with explicit r, s (32-byte little-endian, used
+// un-reduced like the reference's 248-bit values): in = pih, pi_a, pib1 (G1 XYZZ), pi_b (G2 XYZZ), pi_c.
+void groth16_finalize(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                      const void *delta1, const void *delta2, const uint8_t *r32, const uint8_t *s32, void *out256) {
+    const uint8_t *m = (const uint8_t *)msms768;
+    HG1 pih, pi_a, pib1, pi_c;
+    HG2 pi_b;
+    memcpy(&pih, m, 128); memcpy(&pi_a, m + 128, 128); memcpy(&pib1, m + 256, 128);
+    memcpy(&pi_b, m + 384, 256); memcpy(&pi_c, m + 640, 128);
+    HG1Affine a1, b1, d1;
+    HG2Affine b2, d2;
+    memcpy(&a1, alpha1, 64); memcpy(&b1, beta1, 64); memcpy(&d1, delta1, 64);
+    memcpy(&b2, beta2, 128); memcpy(&d2, delta2, 128);
+
+    ec_madd(pi_a, a1);                                   // pi_a += alpha1 + r*delta1      (:222-224)
+    ec_add(pi_a, scalar_mul(d1, r32, 32));
+    ec_madd(pi_b, b2);                                   // pi_b += beta2 + s*delta2       (:226-228)
+    ec_add(pi_b, scalar_mul(d2, s32, 32));
+    ec_madd(pib1, b1);                                   // pib1 += beta1 + s*delta1       (:230-232)
+    ec_add(pib1, scalar_mul(d1, s32, 32));
+    ec_add(pi_c, pih);                                   // pi_c += pih                    (:234)
+    HG1Affine pa = ec_to_affine(pi_a), pb1 = ec_to_affine(pib1);
+    ec_add(pi_c, scalar_mul(pa, s32, 32));               // + s*pi_a                       (:236-237)
+    ec_add(pi_c, scalar_mul(pb1, r32, 32));              // + r*pib1                       (:239-240)
+    HFr r, s;                                            // rs = r*s mod r                 (:242-243)
+    memcpy(&r, r32, 32); memcpy(&s, s32, 32);
+    HFr rs = hfp_to_mont(fmul(r, s));
+    uint8_t rsb[32];
+    memcpy(rsb, &rs, 32);
+    ec_add(pi_c, ec_neg(scalar_mul(d1, rsb, 32)));       // - (rs)*delta1                  (:245-246)
+
+    HG2Affine B = ec_to_affine(pi_b);
+    HG1Affine C = ec_to_affine(pi_c);
+    uint8_t *o = (uint8_t *)out256;
+    memcpy(o, &pa, 64); memcpy(o + 64, &B, 128); memcpy(o + 192, &C, 64);
+}
+
+// canonical decimal string of a Montgomery-form Fq element (RawFq::toString, fr.cpp.ejs:202-213)
+void fq_to_decimal(const void *mont32, char *out80) {
+    HFq x;
+    memcpy(&x, mont32, 32);
+    x = hfp_from_mont(x);
+    uint64_t v[4] = {x.v[0], x.v[1], x.v[2], x.v[3]};
+    char tmp[80];
+    int n = 0;
+    while (v[0] | v[1] | v[2] | v[3]) {
+        unsigned __int128 rem = 0;
+        for (int i = 3; i >= 0; i--) {
+            unsigned __int128 cur = (rem << 64) | v[i];
+            v[i] = (uint64_t)(cur / 10);
+            rem = cur % 10;
+        }
+        tmp[n++] = (char)('0' + (int)rem);
+    }
+    if (n == 0) tmp[n++] = '0';
+    for (int i = 0; i < n; i++) out80[i] = tmp[n - 1 - i];
+    out80[n] = 0;
+}
+}  // namespace b200
+
 extern "C" {
+
+void b200_groth16_finalize(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                           const void *delta1, const void *delta2, const void *r32, const void *s32, void *out256) {
+    b200::groth16_finalize(msms768, alpha1, beta1, beta2, delta1, delta2, (const uint8_t *)r32, (const uint8_t *)s32, out256);
+}
+void b200_fq_to_decimal(const void *mont32, char *out80) { b200::fq_to_decimal(mont32, out80); }
 
 void b200_host_fq_mul(void *r, const void *a, const void *b) { st(r, fp_mul(ld<Fq>(a), ld<Fq>(b))); }
 void b200_host_fq_add(void *r, const void *a, const void *b) { st(r, fp_add(ld<Fq>(a), ld<Fq>(b))); }

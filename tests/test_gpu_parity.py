@@ -234,7 +234,7 @@ def test_ntt_large_roundtrip_and_oracle(ctx, orc, log_n):
     import numpy as np
     n = 1 << log_n
     rng = np.random.default_rng(log_n)
-    raw = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)   # < 2^254 < r: valid field elements
+    raw = rng.integers(0, 1 << 61, size=(n, 4), dtype=np.uint64)   # < 2^253 < r: valid field elements
     data = raw.tobytes()
     fwd = ctx.ntt(data)
     assert ctx.ntt(fwd, inverse=True) == data

@@ -1,0 +1,186 @@
+"""CPU-only tests of everything on the host side of the C-ABI: the library loads and exports every symbol
+include/b200snark.h declares, the host arithmetic (the kernels' own templates compiled for the CPU, and
+the 4x64 host field used for blinding / Horner) equals the oracle, the product refuses to run without a
+GPU, and the CLI / file readers reproduce the reference's error behaviour."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import bn254 as bn
+import oracle_lib
+import synth_util
+import rapidsnark_old_b200 as b200
+from rapidsnark_old_b200 import synth
+
+ROOT = oracle_lib.ROOT
+PROVER = os.path.join(ROOT, "build", "prover")
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200snark.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    L = b200.lib()
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(b200.EXPORTS) <= declared | {"b200_groth16_finalize", "b200_fq_to_decimal"}
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(b200.B200Error) as e:
+        b200.Context(0)
+    assert e.value.code == b200.ERR_NO_GPU
+    assert "no CPU path" in str(e.value)
+
+
+def _call(name, size, *args):
+    out = ctypes.create_string_buffer(size)
+    getattr(b200.lib(), name)(out, *args)
+    return out.raw
+
+
+@pytest.mark.parametrize("name,p", [("fq", bn.Q), ("fr", bn.R_ORDER)])
+def test_device_field_algorithm_on_host(name, p):
+    """The 8x32-limb even/odd Montgomery product of csrc/field.cuh (host build emulates the PTX carry flag)."""
+    r = bn.rng(3)
+    crit = [0, 1, 2, p - 1, p - 2, p // 2, (1 << 253) % p, (1 << 64) - 1, 1 << 64, (1 << 128) - 1, bn.MONT_R % p]
+    vals = crit + [r.randrange(p) for _ in range(300)]
+    rinv = pow(bn.MONT_R, -1, p)
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        ab, bb = a.to_bytes(32, "little"), b.to_bytes(32, "little")
+        assert int.from_bytes(_call("b200_host_%s_mul" % name, 32, ab, bb), "little") == a * b * rinv % p
+        assert int.from_bytes(_call("b200_host_%s_add" % name, 32, ab, bb), "little") == (a + b) % p
+        assert int.from_bytes(_call("b200_host_%s_sub" % name, 32, ab, bb), "little") == (a - b) % p
+        assert int.from_bytes(_call("b200_host_%s_neg" % name, 32, ab), "little") == (-a) % p
+    a = vals[20]
+    assert bn.from_mont(_call("b200_host_%s_inv" % name, 32, bn.to_mont(a, p)), p) == pow(a, -1, p)
+
+
+def test_device_curve_formulas_on_host_vs_oracle():
+    o = oracle_lib.best()
+    r = bn.rng(5)
+    for nm, gb, xs, afs in (("g1", bn.g1_aff_bytes(bn.G1_GEN), 128, 64), ("g2", bn.g2_aff_bytes(bn.G2_GEN), 256, 128)):
+        mul, toaff = getattr(o, nm + "_mul"), getattr(o, nm + "_to_affine")
+        for i in range(12):
+            k1, k2 = r.randrange(bn.R_ORDER), r.randrange(bn.R_ORDER)
+            if i == 0: k2 = k1                      # doubling inside add / madd
+            if i == 1: k2 = bn.R_ORDER - k1         # P + (-P)
+            if i == 2: k2 = 0                       # infinity operand
+            P1, P2 = mul(gb, bn.le32(k1)), mul(gb, bn.le32(k2))
+            A2 = toaff(P2)
+            ref = toaff(getattr(o, nm + "_add")(P1, P2))
+            assert toaff(_call("b200_host_%s_add" % nm, xs, P1, P2)) == ref
+            assert toaff(_call("b200_host_%s_madd" % nm, xs, P1, A2)) == ref
+            assert _call("b200_host_%s_to_affine" % nm, afs, P1) == toaff(P1)
+            assert toaff(_call("b200_host_%s_dbl" % nm, xs, P1)) == toaff(getattr(o, nm + "_dbl")(P1))
+            assert toaff(_call("b200_host_%s_mul" % nm, xs, gb, bn.le32(k1), ctypes.c_uint32(32))) == toaff(P1)
+
+
+def test_fq2_kat_on_host():
+    """alt_bn128_test.cpp:12-29: (2,2)*(3,3) = (0,12)."""
+    e1 = bn.to_mont(2) + bn.to_mont(2)
+    e2 = bn.to_mont(3) + bn.to_mont(3)
+    assert _call("b200_host_fq2_mul", 64, e1, e2) == bn.to_mont(0) + bn.to_mont(12)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_groth16_finalize_equals_oracle_blind(seed):
+    """Host blinding/to-affine (4x64 field) vs the oracle's restatement of groth16.cpp:209-253."""
+    o = oracle_lib.best()
+    s = synth_util.make(4)
+    p = s.points
+    msms = o.prove_msms(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"],
+                        p["H"], s.wtns_bytes())
+    r = bn.rng(seed)
+    rb = r.getrandbits(248).to_bytes(32, "little")
+    sb = r.getrandbits(248).to_bytes(32, "little")
+    vk = s.vk
+    ref = o.blind(msms, vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"], vk["delta2"], rb, sb)
+    out = ctypes.create_string_buffer(256)
+    b200.lib().b200_groth16_finalize(msms, vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"], vk["delta2"], rb, sb, out)
+    assert out.raw == ref
+    # and the proof satisfies the Groth16 equation in the exponent
+    R = synth.R
+    d = s.expected_dlogs()
+    ri, si = int.from_bytes(rb, "little"), int.from_bytes(sb, "little")
+    a = (s.alpha + d["pi_a"] + ri * s.delta) % R
+    assert out.raw[:64] == o.g1_mul_affine(synth.g1_gen_bytes(), a)
+
+
+def test_fq_to_decimal():
+    for v in (0, 1, 10, bn.Q - 1, 12345678901234567890123456789012345678901234567890):
+        buf = ctypes.create_string_buffer(80)
+        b200.lib().b200_fq_to_decimal(bn.to_mont(v % bn.Q), buf)
+        assert buf.value.decode() == str(v % bn.Q)
+
+
+# ----------------------------------------------------------------------------- CLI / readers
+def _run(args):
+    return subprocess.run([PROVER] + args, capture_output=True, text=True)
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("synth")
+    s = synth_util.make(4)
+    zk, wt = d / "c.zkey", d / "w.wtns"
+    zk.write_bytes(synth.zkey_bytes(s))
+    wt.write_bytes(synth.wtns_bytes_file(s))
+    return d, str(zk), str(wt)
+
+
+def test_cli_usage_message():
+    r = _run([])
+    assert r.returncode != 0
+    assert "Usage: prover <circuit.zkey> <witness.wtns> <proof.json> <public.json>" in r.stderr
+
+
+def test_cli_rejects_wrong_magic_and_version(files):
+    d, zk, wt = files
+    r = _run([wt, wt, str(d / "p.json"), str(d / "pub.json")])          # wtns given as zkey
+    assert r.returncode != 0 and "Invalid file type. It should be zkey and it us wtns" in r.stderr
+    bad = d / "v9.zkey"
+    raw = bytearray(open(zk, "rb").read())
+    raw[4:8] = (9).to_bytes(4, "little")
+    bad.write_bytes(bytes(raw))
+    r = _run([str(bad), wt, str(d / "p.json"), str(d / "pub.json")])
+    assert r.returncode != 0 and "Invalid version. It should be <=1 and it us 9" in r.stderr
+
+
+def test_cli_rejects_other_curve_and_protocol(files):
+    d, zk, wt = files
+    raw = bytearray(open(zk, "rb").read())
+    i = raw.index(synth.R.to_bytes(32, "little"))
+    raw[i] ^= 2
+    bad = d / "curve.zkey"
+    bad.write_bytes(bytes(raw))
+    r = _run([str(bad), wt, str(d / "p.json"), str(d / "pub.json")])
+    assert r.returncode != 0 and "zkey curve not supported" in r.stderr
+    raw = bytearray(open(zk, "rb").read())
+    raw[12 + 12] = 2                                      # section 1 payload: protocol id
+    bad = d / "proto.zkey"
+    bad.write_bytes(bytes(raw))
+    r = _run([str(bad), wt, str(d / "p.json"), str(d / "pub.json")])
+    assert r.returncode != 0 and "zkey file is not groth16" in r.stderr
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
+def test_cli_fails_loudly_without_gpu(files):
+    d, zk, wt = files
+    r = _run([zk, wt, str(d / "p.json"), str(d / "pub.json")])
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr
+    assert not os.path.exists(d / "p.json")
