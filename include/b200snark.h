@@ -64,6 +64,9 @@ int b200_msm_g2_dev(b200_ctx *ctx, const void *d_bases_affine, const void *d_sca
                     uint32_t scalar_size, uint64_t n, void *out_xyzz256);
 /* window size override for experiments (0 = automatic) */
 void b200_set_msm_window(b200_ctx *ctx, int c_bits);
+/* tuning knobs for experiments: "msm_window", "acc_smem" (-1 auto / 0 registers / 1 shared memory),
+ * "precomp" (-1 auto / 0 off / 1 on: per-window precomputed tables for resident zkeys), "precomp_c" */
+int b200_set_option(b200_ctx *ctx, const char *name, int value);
 
 /* ---- NTT: replaces FFT<Fr>::fft / ifft (fft.hpp:24-25), natural order in and out ------------------ */
 int b200_ntt_fr(b200_ctx *ctx, void *a_host, uint64_t n, int inverse);

@@ -22,7 +22,7 @@ _u32, _u64, _vp, _int = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctype
 
 EXPORTS = [
     "b200_init", "b200_free", "b200_last_error", "b200_launch_count", "b200_last_phase_ms", "b200_phase_name",
-    "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window",
+    "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window", "b200_set_option",
     "b200_ntt_fr", "b200_ntt_fr_dev",
     "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
     "b200_groth16_finalize", "b200_fq_to_decimal",
@@ -70,6 +70,7 @@ def lib():
         for name in ("b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev"):
             getattr(L, name).argtypes = [_vp, _vp, _vp, _u32, _u64, _vp]
         L.b200_set_msm_window.argtypes = [_vp, _int]
+        L.b200_set_option.argtypes = [_vp, ctypes.c_char_p, _int]
         L.b200_ntt_fr.argtypes = [_vp, _vp, _u64, _int]
         L.b200_ntt_fr_dev.argtypes = [_vp, _vp, _u64, _int]
         L.b200_zkey_upload.argtypes = [_vp, ctypes.POINTER(ZKeyDesc), ctypes.POINTER(_vp)]
@@ -228,6 +229,9 @@ class Context:
 
     def set_msm_window(self, c_bits):
         lib().b200_set_msm_window(self.handle, c_bits)
+
+    def set_option(self, name, value):
+        self._check(lib().b200_set_option(self.handle, name.encode(), int(value)))
 
     # ---- NTT (natural order in/out, Montgomery data)
     def ntt(self, data, inverse=False):

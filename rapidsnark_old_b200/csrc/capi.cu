@@ -44,7 +44,7 @@ void b200_free(b200_ctx *h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *all[] = {&c->w_hist, &c->w_cursor, &c->w_entries, &c->w_buckets, &c->w_partial, &c->w_hot,
-                     &c->w_scan_totals, &c->w_segs, &c->w_win, &c->w_in_bases, &c->w_in_scalars, &c->w_ntt};
+                     &c->w_scan_totals, &c->w_segs, &c->w_win, &c->w_plan, &c->w_tasks, &c->w_in_bases, &c->w_in_scalars, &c->w_ntt};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t ev : c->evpool) cudaEventDestroy(ev);
@@ -57,6 +57,15 @@ const char *b200_last_error(b200_ctx *h) { return h ? h->c.err.c_str() : g_init_
 uint64_t b200_launch_count(b200_ctx *h) { return h ? h->c.launches : 0; }
 void *b200_stream(b200_ctx *h) { return h ? (void *)h->c.stream : nullptr; }
 void b200_set_msm_window(b200_ctx *h, int c_bits) { if (h) h->c.force_c = c_bits; }
+int b200_set_option(b200_ctx *h, const char *name, int value) {
+    if (!h || !name) return B200_ERR_ARG;
+    if (!strcmp(name, "msm_window")) h->c.force_c = value;
+    else if (!strcmp(name, "acc_smem")) h->c.opt_acc_smem = value;
+    else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;
+    else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;
+    else { h->c.err = std::string("unknown option ") + name; return B200_ERR_ARG; }
+    return B200_OK;
+}
 
 int b200_last_phase_ms(b200_ctx *h, float *out, int cap) {
     if (!h || !out) return 0;

@@ -36,6 +36,9 @@ struct Ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     int force_c = 0;
+    int opt_acc_smem = -1;   // -1 auto, 0 registers, 1 shared memory (experiments)
+    int opt_precomp = -1;    // -1 auto (on), 0 off; window bits of resident tables in opt_precomp_c
+    int opt_precomp_c = 0;
     float phase_ms[PH_COUNT] = {0};
     struct Seg { int ph, e0, e1; };
     std::vector<cudaEvent_t> evpool;   // phase timing events (reused call after call)
@@ -44,7 +47,7 @@ struct Ctx {
     std::vector<DevBuf *> bufs;  // everything to free
 
     // MSM workspaces (shared by G1/G2 calls; grow-only)
-    DevBuf w_hist, w_cursor, w_entries, w_buckets, w_partial, w_hot, w_scan_totals, w_segs, w_win;
+    DevBuf w_hist, w_cursor, w_entries, w_buckets, w_partial, w_hot, w_scan_totals, w_segs, w_win, w_plan, w_tasks;
     DevBuf w_in_bases, w_in_scalars;   // staging for host-pointer calls
     DevBuf w_ntt;                      // staging for host-pointer NTT calls
     void *pinned = nullptr;            // small pinned host buffer for results
@@ -150,8 +153,18 @@ void host_horner_g1(const void *win, int nwin, int c, void *out);   // src/hostm
 void host_horner_g2(const void *win, int nwin, int c, void *out);
 
 // msm entry points implemented in msm_g1.cu / msm_g2.cu
-int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G1Xyzz *out_host);
-int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G2Xyzz *out_host);
+struct MsmTableRaw {        // resident per-window table 2^(c*j) * P_i (see msm.cuh); tbl == nullptr: none
+    const void *tbl = nullptr;
+    u32 n = 0;
+    int c = 0, nwin = 0;
+};
+int msm_table_windows(int c);   // rows of a table for 32-byte scalars
+int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G1Xyzz *out_host,
+               const MsmTableRaw *table = nullptr);
+int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G2Xyzz *out_host,
+               const MsmTableRaw *table = nullptr);
+int msm_g1_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl);
+int msm_g2_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl);
 
 }  // namespace b200
 

@@ -74,32 +74,58 @@ HD_COLD Xyzz<F> ec_dbl(const Xyzz<F> &p) {
     return r;
 }
 
-// acc += q (q affine)   (madd-2008-s: 8M + 2S)
+// Accumulator held in registers.  ec_madd is written against this small accessor interface so the hot
+// kernel can also keep the running bucket sum in shared memory (SmemAcc in msm.cuh) and hold only the
+// temporaries of one mixed addition in registers.
 template <class F>
-HD void ec_madd(Xyzz<F> &acc, const Affine<F> &q) {
+struct RegAcc {
+    Xyzz<F> p;
+    HD F ld_x() const { return p.x; }
+    HD F ld_y() const { return p.y; }
+    HD F ld_zz() const { return p.zz; }
+    HD F ld_zzz() const { return p.zzz; }
+    HD void st_x(const F &v) { p.x = v; }
+    HD void st_y(const F &v) { p.y = v; }
+    HD void st_zz(const F &v) { p.zz = v; }
+    HD void st_zzz(const F &v) { p.zzz = v; }
+    HD void st_all(const Xyzz<F> &v) { p = v; }
+    HD Xyzz<F> get() const { return p; }
+};
+
+// acc += q (q affine)   (madd-2008-s: 8M + 2S)
+template <class Acc, class F>
+HD void ec_madd_acc(Acc &acc, const Affine<F> &q) {
     if (q.is_zero()) return;
-    if (acc.is_zero()) {
-        acc.x = q.x; acc.y = q.y; acc.zz = F::one(); acc.zzz = F::one();
+    F zz = acc.ld_zz();
+    if (zz.is_zero()) {
+        acc.st_x(q.x); acc.st_y(q.y); acc.st_zz(F::one()); acc.st_zzz(F::one());
         return;
     }
-    F u2 = fmul(q.x, acc.zz);
-    F s2 = fmul(q.y, acc.zzz);
-    F p = fsub(u2, acc.x);
-    F r = fsub(s2, acc.y);
+    F zzz = acc.ld_zzz();
+    F x1 = acc.ld_x(), y1 = acc.ld_y();
+    F p = fsub(fmul(q.x, zz), x1);
+    F r = fsub(fmul(q.y, zzz), y1);
     if (p.is_zero()) {
-        if (r.is_zero()) acc = ec_dbl_affine(q);   // same point
-        else acc = Xyzz<F>::zero();                 // opposite points
+        if (r.is_zero()) acc.st_all(ec_dbl_affine(q));   // same point
+        else acc.st_all(Xyzz<F>::zero());                 // opposite points
         return;
     }
     F pp = fsqr(p);
     F ppp = fmul(p, pp);
-    F qq = fmul(acc.x, pp);
+    acc.st_zz(fmul(zz, pp));
+    acc.st_zzz(fmul(zzz, ppp));
+    F qq = fmul(x1, pp);
     F x3 = fsub(fsub(fsqr(r), ppp), fdbl(qq));
-    F y3 = fsub(fmul(r, fsub(qq, x3)), fmul(acc.y, ppp));
-    acc.x = x3;
-    acc.y = y3;
-    acc.zz = fmul(acc.zz, pp);
-    acc.zzz = fmul(acc.zzz, ppp);
+    acc.st_x(x3);
+    acc.st_y(fsub(fmul(r, fsub(qq, x3)), fmul(y1, ppp)));
+}
+
+template <class F>
+HD void ec_madd(Xyzz<F> &acc, const Affine<F> &q) {
+    RegAcc<F> a;
+    a.p = acc;
+    ec_madd_acc(a, q);
+    acc = a.p;
 }
 
 // acc += q   (add-2008-s: 12M + 2S)

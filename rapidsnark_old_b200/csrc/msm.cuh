@@ -10,25 +10,31 @@
 //   2. k_scan_*             exclusive scan of the histogram -> bucket offsets
 //   3. k_msm_digits<true>   scatter of (point index | sign) into bucket order: a counting sort, so
 //                           the order inside a bucket is arbitrary - the group sum does not care
-//   4. k_msm_accumulate     THE hot kernel: the sorted entry list is cut into equal chunks of T
-//                           entries, one per thread, regardless of bucket boundaries; each thread
-//                           gathers its affine points (64 B / 128 B, read-only path, next point
-//                           prefetched while the current mixed add runs) and flushes the running
-//                           XYZZ sum whenever the bucket id changes.  Equal chunks = no divergence
-//                           in trip count, and skewed witnesses (huge |digit| = 1 buckets) are split
-//                           over many threads for free.  Buckets cut by a chunk boundary go to
-//                           per-thread head/tail partial slots.
-//   5. k_msm_merge / k_msm_merge_hot  fold those partials (a bucket spanning > 32 chunks is folded
-//                           by a whole CTA: strided partial sums + shared-memory tree)
+//   4. k_msm_plan_*         task list: one task per bucket, buckets larger than CAP entries are cut
+//                           into CAP-sized sub-tasks; tasks are counting-sorted by length (longest
+//                           first) so the 32 lanes of a warp run equally long loops and the long
+//                           tasks start first
+//   5. k_msm_accumulate     THE hot kernel, one thread per task: gathers its affine points (64 B /
+//                           128 B each, read-only path, next point prefetched while the current
+//                           mixed addition runs) into an XYZZ running sum and writes the bucket.
+//                           Skewed witnesses (huge |digit| = 1 buckets) become many sub-tasks whose
+//                           partial sums are folded by k_msm_merge_hot (one CTA per hot bucket:
+//                           strided partial sums + shared-memory tree)
 //   6. k_msm_reduce_segments / k_msm_window_sum   sum_k k*B_k per window: running sums over
 //                           segments of L buckets + small in-thread multiplier, then a CTA tree
 //   7. host: Horner over the <= 65 window sums (a serial chain of ~270 group operations is ~8x
 //      faster on one CPU core than on one GPU thread)
 //
+// Resident tables (zkey point sections are static): k_msm_precompute stores 2^(c*j) * P_i for every
+// window j next to the original points, once, at upload time.  All windows then share ONE bucket
+// set (digit j of point i is an entry for table point j*n + i), so steps 6-7 shrink by the window
+// count and c can grow; only the gather in step 5 touches the larger table.
+//
 // Zero scalars/digits are skipped like the reference (multiexp.cpp:43); zero bases (0,0) are skipped
 // inside the mixed add (multiexp.cpp:40).  Scalars are read as plain 8*scalar_size-bit integers and
 // never reduced (multiexp.cpp:118).
 #pragma once
+#include <type_traits>
 #include "ctx.cuh"
 #include "memops.cuh"
 
@@ -38,30 +44,38 @@ struct MsmGeom {
     int c;          // window bits
     int nwin;       // windows (covers nbits + 1 for the signed-digit carry)
     u32 nbk;        // buckets per window = 2^(c-1)
-    u32 NB;         // nwin * nbk
-    u32 T;          // entries per accumulate thread
+    u32 nwin_b;     // bucket sets: nwin, or 1 when all windows share one set (precomputed tables)
+    u32 NB;         // nwin_b * nbk
+    u32 CAP;        // max entries per accumulate task
     u32 L;          // buckets per reduce segment
-    u32 nseg;       // segments per window
+    u32 nseg;       // segments per bucket set
 };
 
-static const u32 MSM_MAX_BATCH = 1u << 24;   // points per sort batch (entry index fits 31 bits, entries < 2^32)
-static const int MSM_HOT_SPAN = 32;          // chunks; wider buckets are merged by a CTA
+static const u32 MSM_MAX_BATCH = 1u << 24;   // points per sort batch (entries < 2^32, entry index < 2^31)
 static const int MSM_MAX_WIN = 65;
+static const u32 MSM_MAX_CAP = 2048;         // task-length histogram has MSM_MAX_CAP + 1 <= 4096 bins
 
-inline MsmGeom msm_geometry(uint64_t n, uint32_t scalar_size, int force_c) {
-    MsmGeom g;
+inline int msm_auto_c(uint64_t n) {
     int lg = 0;
     while ((2ull << lg) <= n) lg++;   // floor(log2 n)
-    int c = lg - 4;
+    int c = lg - 5;                   // measured on B200: 2^20 points -> c = 14..15
     if (c < 4) c = 4;
     if (c > 16) c = 16;
-    if (force_c >= 4 && force_c <= 20) c = force_c;
+    return c;
+}
+
+inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool shared_buckets) {
+    MsmGeom g;
     int nbits = (int)scalar_size * 8;
     g.c = c;
     g.nwin = (nbits + c) / c;         // ceil((nbits + 1) / c)
     g.nbk = 1u << (c - 1);
-    g.NB = (u32)g.nwin * g.nbk;
-    g.T = 32;
+    g.nwin_b = shared_buckets ? 1u : (u32)g.nwin;
+    g.NB = g.nwin_b * g.nbk;
+    uint64_t avg = n_batch * (uint64_t)g.nwin / g.NB + 1;
+    u32 cap = 256;
+    while (cap < 4 * avg && cap < MSM_MAX_CAP) cap <<= 1;
+    g.CAP = cap;
     g.L = g.nbk >= 16 ? 16 : g.nbk;
     g.nseg = g.nbk / g.L;
     return g;
@@ -72,8 +86,8 @@ inline MsmGeom msm_geometry(uint64_t n, uint32_t scalar_size, int force_c) {
 // ------------------------------------------------------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint8_t *__restrict__ scalars, u32 scalar_size, u32 n,
-                                                      int c, int nwin, u32 nbk, u32 *__restrict__ counters,
-                                                      u32 *__restrict__ entries) {
+                                                      int c, int nwin, u32 nbk, u32 shared_buckets, u32 table_stride,
+                                                      u32 *__restrict__ counters, u32 *__restrict__ entries) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 s[9];
@@ -108,12 +122,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint8_t *__restrict__ 
         u32 mag = neg ? (1u << c) - raw : raw;          // raw == 2^c -> digit 0, carry 1
         carry = neg;
         if (mag != 0) {
-            u32 b = (u32)w * nbk + mag - 1;
+            u32 b = (shared_buckets ? 0u : (u32)w * nbk) + mag - 1;
             if (!SCATTER) {
                 atomicAdd(&counters[b], 1u);
             } else {
                 u32 pos = atomicAdd(&counters[b], 1u);
-                entries[pos] = i | (neg << 31);
+                // table point of (window w, point i): w * table_stride + i  (table_stride = 0: plain bases)
+                entries[pos] = ((u32)w * table_stride + i) | (neg << 31);
             }
         }
     }
@@ -203,93 +218,119 @@ static __global__ void __launch_bounds__(1024) k_scan_add(u32 *__restrict__ data
 }
 
 // ------------------------------------------------------------------------------------------------
-// 4: bucket accumulation over equal chunks of the sorted entry list
+// 4: task plan - buckets (or CAP-sized pieces of big buckets) sorted by length, longest first
 // ------------------------------------------------------------------------------------------------
-template <class F, bool PREFETCH_REGS>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<F> *__restrict__ bases,
-                                                          const u32 *__restrict__ entries,
-                                                          const u32 *__restrict__ off, u32 NB, u32 T,
-                                                          Xyzz<F> *__restrict__ buckets,
-                                                          Xyzz<F> *__restrict__ partial, int add_existing) {
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 E = off[NB];
-    const u64 start64 = (u64)t * T;
-    if (start64 >= E) return;
-    const u32 start = (u32)start64;
-    const u32 end = (E - start < T) ? E : start + T;
-
-    // bucket containing `start`: the largest b with off[b] <= start
-    u32 lo = 0, hi = NB - 1;
-    while (lo < hi) {
-        u32 mid = (lo + hi + 1) >> 1;
-        if (off[mid] <= start) lo = mid; else hi = mid - 1;
+// plan[0] = hot partial slots allocated, plan[1] = number of hot buckets
+static __global__ void __launch_bounds__(256) k_msm_plan_count(const u32 *__restrict__ off, u32 NB, u32 CAP,
+                                                          u32 *__restrict__ lenhist /* [4096], index CAP_MAX - len */,
+                                                          u32 *__restrict__ plan, u32 *__restrict__ hot_base,
+                                                          u32 *__restrict__ hot_list) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    u32 cnt = off[b + 1] - off[b];
+    if (cnt == 0) return;
+    u32 nfull = cnt / CAP, rem = cnt - nfull * CAP;
+    if (nfull) atomicAdd(&lenhist[MSM_MAX_CAP - CAP], nfull);
+    if (rem) atomicAdd(&lenhist[MSM_MAX_CAP - rem], 1u);
+    u32 ntask = nfull + (rem ? 1u : 0u);
+    if (ntask > 1) {
+        hot_base[b] = atomicAdd(&plan[0], ntask);
+        hot_list[atomicAdd(&plan[1], 1u)] = b;
     }
-    u32 b = lo;
-    u32 b_end = off[b + 1];
-    bool head = off[b] < start;      // this bucket began in an earlier chunk
+}
 
-    Xyzz<F> acc = Xyzz<F>::zero();
-    u32 e_next = entries[start];
-    Affine<F> p_next;
-    if (PREFETCH_REGS) p_next = ldg_struct(bases + (e_next & 0x7fffffffu));
-
-    for (u32 pos = start; pos < end; pos++) {
-        if (pos >= b_end) {
-            // bucket b is finished inside this chunk
-            if (head) st_struct(partial + 2 * (size_t)t, acc);
-            else {
-                if (add_existing) { Xyzz<F> old = ld_struct(buckets + b); ec_add(acc, old); }
-                st_struct(buckets + b, acc);
-            }
-            head = false;
-            acc = Xyzz<F>::zero();
-            do { b++; b_end = off[b + 1]; } while (pos >= b_end);
-        }
-        u32 e = e_next;
-        Affine<F> p;
-        if (PREFETCH_REGS) p = p_next; else p = ldg_struct(bases + (e & 0x7fffffffu));
-        if (pos + 1 < end) {
-            e_next = entries[pos + 1];
-            if (PREFETCH_REGS) p_next = ldg_struct(bases + (e_next & 0x7fffffffu));
-        }
-        if (e >> 31) p.y = fneg(p.y);
-        ec_madd(acc, p);
+static __global__ void __launch_bounds__(256) k_msm_plan_place(const u32 *__restrict__ off, u32 NB, u32 CAP,
+                                                          u32 *__restrict__ cursor /* scanned lenhist */,
+                                                          uint2 *__restrict__ tasks) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    u32 cnt = off[b + 1] - off[b];
+    if (cnt == 0) return;
+    u32 nfull = cnt / CAP, rem = cnt - nfull * CAP;
+    if (nfull) {
+        u32 pos = atomicAdd(&cursor[MSM_MAX_CAP - CAP], nfull);
+        for (u32 j = 0; j < nfull; j++) tasks[pos + j] = make_uint2(b, j);
     }
-    // last bucket of the chunk
-    if (head) st_struct(partial + 2 * (size_t)t, acc);                  // spans the whole chunk or ends in it
-    else if (b_end > end) st_struct(partial + 2 * (size_t)t + 1, acc);  // continues into the next chunk
-    else {
-        if (add_existing) { Xyzz<F> old = ld_struct(buckets + b); ec_add(acc, old); }
-        st_struct(buckets + b, acc);
+    if (rem) {
+        u32 pos = atomicAdd(&cursor[MSM_MAX_CAP - rem], 1u);
+        tasks[pos] = make_uint2(b, nfull);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// 5: fold the partials of buckets cut by chunk boundaries
+// 5: bucket accumulation, one thread per task
 // ------------------------------------------------------------------------------------------------
+// running sum in shared memory: field k of thread t lives at base[k * blockDim.x + t] (16-byte units), so a
+// warp's 128-bit accesses are conflict-free; only one mixed addition's temporaries stay in registers
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_merge(const u32 *__restrict__ off, u32 NB, u32 T,
-                                                     Xyzz<F> *__restrict__ buckets,
-                                                     const Xyzz<F> *__restrict__ partial, int add_existing,
-                                                     u32 *__restrict__ hot /* [0] = count, then bucket ids */) {
-    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= NB) return;
-    u32 o0 = off[b], o1 = off[b + 1];
-    if (o1 == o0) return;
-    u32 t0 = o0 / T, t1 = (o1 - 1) / T;
-    if (t0 == t1) return;                      // written directly by the accumulate kernel
-    if (t1 - t0 > (u32)MSM_HOT_SPAN) {
-        u32 k = atomicAdd(&hot[0], 1u);
-        hot[1 + k] = b;
-        return;
+struct SmemAcc {
+    uint4 *base;   // already offset by threadIdx.x
+    static const int FV = sizeof(F) / 16;
+    DEVFN F ld(int field) const {
+        F r;
+        uint4 *d = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+        for (int i = 0; i < FV; i++) d[i] = base[(field * FV + i) * blockDim.x];
+        return r;
     }
-    Xyzz<F> acc = ld_struct(partial + 2 * (size_t)t0 + 1);
-    for (u32 t = t0 + 1; t <= t1; t++) {
-        Xyzz<F> q = ld_struct(partial + 2 * (size_t)t);
-        ec_add(acc, q);
+    DEVFN void st(int field, const F &v) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(&v);
+#pragma unroll
+        for (int i = 0; i < FV; i++) base[(field * FV + i) * blockDim.x] = s[i];
     }
-    if (add_existing) { Xyzz<F> old = ld_struct(buckets + b); ec_add(acc, old); }
-    st_struct(buckets + b, acc);
+    DEVFN F ld_x() const { return ld(0); }
+    DEVFN F ld_y() const { return ld(1); }
+    DEVFN F ld_zz() const { return ld(2); }
+    DEVFN F ld_zzz() const { return ld(3); }
+    DEVFN void st_x(const F &v) { st(0, v); }
+    DEVFN void st_y(const F &v) { st(1, v); }
+    DEVFN void st_zz(const F &v) { st(2, v); }
+    DEVFN void st_zzz(const F &v) { st(3, v); }
+    DEVFN void st_all(const Xyzz<F> &v) { st(0, v.x); st(1, v.y); st(2, v.zz); st(3, v.zzz); }
+    DEVFN Xyzz<F> get() const { Xyzz<F> r; r.x = ld(0); r.y = ld(1); r.zz = ld(2); r.zzz = ld(3); return r; }
+};
+
+template <class F, bool ACC_SMEM, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F> *__restrict__ bases,
+                                                                const u32 *__restrict__ entries,
+                                                                const u32 *__restrict__ off,
+                                                                const uint2 *__restrict__ tasks,
+                                                                const u32 *__restrict__ ntasks_ptr, u32 CAP,
+                                                                const u32 *__restrict__ hot_base,
+                                                                Xyzz<F> *__restrict__ buckets,
+                                                                Xyzz<F> *__restrict__ partial, int add_existing) {
+    extern __shared__ uint4 smem_raw[];
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *ntasks_ptr) return;
+    const uint2 task = tasks[t];
+    const u32 b = task.x;
+    const u32 o0 = off[b], cnt = off[b + 1] - o0;
+    const u32 start = o0 + task.y * CAP;
+    const u32 len = (cnt - task.y * CAP < CAP) ? cnt - task.y * CAP : CAP;
+
+    typename std::conditional<ACC_SMEM, SmemAcc<F>, RegAcc<F>>::type acc;
+    if constexpr (ACC_SMEM) acc.base = smem_raw + threadIdx.x;
+    acc.st_all(Xyzz<F>::zero());
+
+    u32 e_next = entries[start];
+    Affine<F> p_next = ldg_struct(bases + (e_next & 0x7fffffffu));
+    for (u32 k = 0; k < len; k++) {
+        u32 e = e_next;
+        Affine<F> p = p_next;
+        if (k + 1 < len) {
+            e_next = entries[start + k + 1];
+            p_next = ldg_struct(bases + (e_next & 0x7fffffffu));
+        }
+        if (e >> 31) p.y = fneg(p.y);
+        ec_madd_acc(acc, p);
+    }
+    Xyzz<F> r = acc.get();
+    if (cnt <= CAP) {
+        if (add_existing) { Xyzz<F> old = ld_struct(buckets + b); ec_add(r, old); }
+        st_struct(buckets + b, r);
+    } else {
+        st_struct(partial + hot_base[b] + task.y, r);
+    }
 }
 
 // CTA-wide tree sum of one XYZZ point per thread; result valid in thread 0.  smem: blockDim.x points
@@ -307,21 +348,22 @@ DEVFN void cta_tree_sum(Xyzz<F> &acc, Xyzz<F> *sm) {
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_merge_hot(const u32 *__restrict__ off, u32 T,
+__global__ void __launch_bounds__(128) k_msm_merge_hot(const u32 *__restrict__ off, u32 CAP,
                                                          Xyzz<F> *__restrict__ buckets,
                                                          const Xyzz<F> *__restrict__ partial, int add_existing,
-                                                         const u32 *__restrict__ hot) {
+                                                         const u32 *__restrict__ plan, const u32 *__restrict__ hot_base,
+                                                         const u32 *__restrict__ hot_list) {
     extern __shared__ uint4 smem_raw[];
     Xyzz<F> *sm = reinterpret_cast<Xyzz<F> *>(smem_raw);
-    u32 nhot = hot[0];
+    const u32 nhot = plan[1];
     for (u32 h = blockIdx.x; h < nhot; h += gridDim.x) {
-        u32 b = hot[1 + h];
-        u32 o0 = off[b], o1 = off[b + 1];
-        u32 t0 = o0 / T, t1 = (o1 - 1) / T;
+        const u32 b = hot_list[h];
+        const u32 cnt = off[b + 1] - off[b];
+        const u32 ntask = (cnt + CAP - 1) / CAP;
+        const Xyzz<F> *src = partial + hot_base[b];
         Xyzz<F> acc = Xyzz<F>::zero();
-        if (threadIdx.x == 0) acc = ld_struct(partial + 2 * (size_t)t0 + 1);
-        for (u32 t = t0 + 1 + threadIdx.x; t <= t1; t += blockDim.x) {
-            Xyzz<F> q = ld_struct(partial + 2 * (size_t)t);
+        for (u32 j = threadIdx.x; j < ntask; j += blockDim.x) {
+            Xyzz<F> q = ld_struct(src + j);
             ec_add(acc, q);
         }
         cta_tree_sum(acc, sm);
@@ -375,44 +417,112 @@ __global__ void __launch_bounds__(128) k_msm_window_sum(const Xyzz<F> *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// resident tables: tbl[j * n + i] = 2^(c*j) * P_i (affine), j < nwin; row 0 is a copy of the points
+// ------------------------------------------------------------------------------------------------
+static const int MSM_PRE_MAX_WIN = 24;   // tables are only built for c >= 11
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_precompute(const Affine<F> *__restrict__ pts, u32 n, int c, int nwin,
+                                                          Affine<F> *__restrict__ tbl) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = ldg_struct(pts + i);
+    st_struct(tbl + i, p);
+    Xyzz<F> q[MSM_PRE_MAX_WIN];   // local memory: 2^(c*j) * P, j = 1..nwin-1, still in XYZZ
+    F pref[MSM_PRE_MAX_WIN];      // running products of zz*zzz for one shared inversion (Montgomery's trick)
+    Xyzz<F> cur = Xyzz<F>::from_affine(p);
+    F run = F::one();
+    for (int j = 1; j < nwin; j++) {
+        for (int k = 0; k < c; k++) cur = ec_dbl(cur);
+        q[j] = cur;
+        if (!cur.is_zero()) run = fmul(run, fmul(cur.zz, cur.zzz));
+        pref[j] = run;
+    }
+    F inv = finv(run);
+    for (int j = nwin - 1; j >= 1; j--) {
+        Affine<F> a;
+        if (q[j].is_zero()) { a.x = F::zero(); a.y = F::zero(); }
+        else {
+            F before = (j > 1) ? pref[j - 1] : F::one();
+            F iz = fmul(inv, before);                       // 1 / (zz_j * zzz_j)
+            inv = fmul(inv, fmul(q[j].zz, q[j].zzz));
+            a.x = fmul(q[j].x, fmul(iz, q[j].zzz));
+            a.y = fmul(q[j].y, fmul(iz, q[j].zz));
+        }
+        st_struct(tbl + (size_t)j * n + i, a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
 template <class F>
+struct MsmTable {          // resident precomputed table (nullptr tbl: plain bases, no precomputation)
+    const Affine<F> *tbl = nullptr;
+    u32 n = 0;             // points per row
+    int c = 0, nwin = 0;   // geometry the table was built for (scalar_size = 32)
+};
+
+template <class F>
+int msm_precompute_table(Ctx *ctx, const Affine<F> *d_pts, u32 n, int c, Affine<F> *d_tbl) {
+    MsmGeom g = msm_geometry(n, 32, c, true);
+    if (n == 0) return B200_OK;
+    if (g.nwin > MSM_PRE_MAX_WIN) { ctx->err = "msm: window too small for a precomputed table"; return B200_ERR_ARG; }
+    B200_LAUNCH(ctx, k_msm_precompute<F>, (n + 127) / 128, 128, 0, d_pts, n, c, g.nwin, d_tbl);
+    return B200_OK;
+}
+
+template <class F>
 int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint32_t scalar_size, uint64_t n,
-                 Xyzz<F> *out_host) {
+                 Xyzz<F> *out_host, const MsmTable<F> *table = nullptr) {
     typedef Xyzz<F> Pt;
     *out_host = Pt::zero();
     if (n == 0) return B200_OK;
     if (scalar_size == 0 || scalar_size > 32) { ctx->err = "msm: scalar_size must be 1..32 bytes"; return B200_ERR_ARG; }
     if (!d_bases_v || !d_scalars_v) { ctx->err = "msm: null input"; return B200_ERR_ARG; }
-    const Affine<F> *d_bases = static_cast<const Affine<F> *>(d_bases_v);
+    const bool pre = table && table->tbl;
+    const Affine<F> *d_bases = pre ? table->tbl : static_cast<const Affine<F> *>(d_bases_v);
     const uint8_t *d_scalars = static_cast<const uint8_t *>(d_scalars_v);
+    if (pre && (n != table->n || scalar_size != 32 || n > MSM_MAX_BATCH)) { ctx->err = "msm: table geometry mismatch"; return B200_ERR_ARG; }
 
-    MsmGeom g = msm_geometry(n, scalar_size, ctx->force_c);
-    if (g.nwin > MSM_MAX_WIN) { ctx->err = "msm: too many windows"; return B200_ERR_ARG; }
     const u32 batch_max = n < MSM_MAX_BATCH ? (u32)n : MSM_MAX_BATCH;
+    int c = pre ? table->c : msm_auto_c(n);
+    if (!pre && ctx->force_c >= 4 && ctx->force_c <= 20) c = ctx->force_c;
+    MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre);
+    if (g.nwin > MSM_MAX_WIN) { ctx->err = "msm: too many windows"; return B200_ERR_ARG; }
+    if (pre && (uint64_t)g.nwin * n >= (1ull << 31)) { ctx->err = "msm: table too large for 31-bit entries"; return B200_ERR_ARG; }
     const size_t hist_len = ((size_t)g.NB + 1 + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
     const u32 ntiles = (u32)(hist_len / SCAN_TILE);
     const size_t max_entries = (size_t)batch_max * g.nwin;
-    const size_t max_chunks = (max_entries + g.T - 1) / g.T;
-    const u32 total_segs = (u32)g.nwin * g.nseg;
+    const size_t max_tasks = (max_entries < g.NB ? max_entries : g.NB) + max_entries / g.CAP + 1;
+    const size_t max_partials = 2 * (max_entries / g.CAP) + 2;
+    const u32 total_segs = g.nwin_b * g.nseg;
 
     B200_TRY(ctx_reserve(ctx, ctx->w_hist, hist_len * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_cursor, hist_len * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_scan_totals, (size_t)ntiles * 4 + 16));
     B200_TRY(ctx_reserve(ctx, ctx->w_entries, max_entries * 4 + 16));
     B200_TRY(ctx_reserve(ctx, ctx->w_buckets, (size_t)g.NB * sizeof(Pt)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_partial, max_chunks * 2 * sizeof(Pt)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_hot, ((size_t)g.NB + 1) * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_partial, max_partials * sizeof(Pt)));
+    B200_TRY(ctx_reserve(ctx, ctx->w_hot, ((size_t)2 * g.NB + 8) * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_plan, (size_t)(2 * SCAN_TILE + 16) * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_tasks, max_tasks * sizeof(uint2)));
     B200_TRY(ctx_reserve(ctx, ctx->w_segs, (size_t)total_segs * sizeof(Pt)));
     B200_TRY(ctx_reserve(ctx, ctx->w_win, (size_t)MSM_MAX_WIN * sizeof(Pt)));
     B200_TRY(ctx_pinned(ctx, (size_t)MSM_MAX_WIN * sizeof(G2Xyzz)));
 
     u32 *d_hist = (u32 *)ctx->w_hist.p, *d_cursor = (u32 *)ctx->w_cursor.p, *d_totals = (u32 *)ctx->w_scan_totals.p;
-    u32 *d_entries = (u32 *)ctx->w_entries.p, *d_hot = (u32 *)ctx->w_hot.p;
+    u32 *d_entries = (u32 *)ctx->w_entries.p;
+    u32 *d_hot_base = (u32 *)ctx->w_hot.p, *d_hot_list = d_hot_base + g.NB;
+    // plan buffer: [0..4095] task-length histogram (then its scan), [4096..8191] scan cursors, [8192..] counters
+    u32 *d_lenhist = (u32 *)ctx->w_plan.p, *d_lencur = d_lenhist + SCAN_TILE, *d_plan = d_lenhist + 2 * SCAN_TILE;
+    uint2 *d_tasks = (uint2 *)ctx->w_tasks.p;
     Pt *d_buckets = (Pt *)ctx->w_buckets.p, *d_partial = (Pt *)ctx->w_partial.p;
     Pt *d_segs = (Pt *)ctx->w_segs.p, *d_win = (Pt *)ctx->w_win.p;
     cudaStream_t st = ctx->stream;
+    const bool g2 = sizeof(F) != 32;
+    const bool acc_smem = ctx->opt_acc_smem >= 0 ? (ctx->opt_acc_smem != 0) : g2;   // default: G2 only
+    const size_t acc_smem_bytes = 128 * sizeof(Pt);
 
     B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_buckets, 0, (size_t)g.NB * sizeof(Pt), st));
 
@@ -420,45 +530,59 @@ int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint3
     for (uint64_t base = 0; base < n; base += batch_max, batch_idx++) {
         const u32 nb = (u32)((n - base < batch_max) ? (n - base) : batch_max);
         const uint8_t *sc = d_scalars + (size_t)base * scalar_size;
-        const Affine<F> *bs = d_bases + base;
+        const Affine<F> *bs = pre ? d_bases : d_bases + base;
         const u32 dgrid = (nb + 255) / 256;
+        const u32 tstride = pre ? table->n : 0;
+        const int add_existing = batch_idx > 0 ? 1 : 0;
 
         phase_begin(ctx, PH_MSM_SORT);
         B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_hist, 0, hist_len * 4, st));
-        B200_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, d_hist, (u32 *)nullptr);
+        B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_lenhist, 0, (size_t)(2 * SCAN_TILE + 16) * 4, st));
+        B200_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_hist, (u32 *)nullptr);
         B200_LAUNCH(ctx, k_scan_tile, ntiles, 1024, 0, d_hist, d_totals);
         B200_LAUNCH(ctx, k_scan_totals, 1, 1024, 0, d_totals, ntiles);
         B200_LAUNCH(ctx, k_scan_add, ntiles, 1024, 0, d_hist, d_totals, d_cursor);
-        B200_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, d_cursor, d_entries);
+        B200_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_cursor, d_entries);
+        // task plan: histogram of task lengths (descending), scan, placement
+        B200_LAUNCH(ctx, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list);
+        B200_LAUNCH(ctx, k_scan_tile, 1, 1024, 0, d_lenhist, d_plan + 2);      // d_plan[2] = number of tasks
+        B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, st));
+        B200_LAUNCH(ctx, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
         phase_end(ctx);
 
-        phase_begin(ctx, sizeof(F) == 32 ? PH_MSM_ACCUM : PH_MSM_ACCUM_G2);
-        const size_t chunks = ((size_t)nb * g.nwin + g.T - 1) / g.T;
-        const u32 agrid = (u32)((chunks + 127) / 128);
-        auto kacc = k_msm_accumulate<F, (sizeof(F) == 32)>;
-        B200_LAUNCH(ctx, kacc, agrid, 128, 0, bs, d_entries, d_hist, g.NB, g.T, d_buckets, d_partial, batch_idx > 0 ? 1 : 0);
+        phase_begin(ctx, g2 ? PH_MSM_ACCUM_G2 : PH_MSM_ACCUM);
+        const size_t ent = (size_t)nb * g.nwin;
+        const size_t tasks_ub = (ent < g.NB ? ent : g.NB) + ent / g.CAP + 1;
+        const u32 agrid = (u32)((tasks_ub + 127) / 128);
+        {
+            // variants: running sum in registers (G1 default) or in shared memory (G2 default: 64-register sum)
+            void (*kacc)(const Affine<F> *, const u32 *, const u32 *, const uint2 *, const u32 *, u32, const u32 *, Pt *, Pt *, int);
+            size_t smem = 0;
+            if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
+            else { kacc = g2 ? k_msm_accumulate<F, false, 2> : k_msm_accumulate<F, false, 3>; }
+            B200_LAUNCH(ctx, kacc, agrid, 128, smem, bs, d_entries, d_hist, d_tasks, d_plan + 2, g.CAP, d_hot_base, d_buckets, d_partial, add_existing);
+        }
         phase_end(ctx);
 
         phase_begin(ctx, PH_MSM_MERGE);
-        B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_hot, 0, 4, st));
-        B200_LAUNCH(ctx, k_msm_merge<F>, (g.NB + 127) / 128, 128, 0, d_hist, g.NB, g.T, d_buckets, d_partial, batch_idx > 0 ? 1 : 0, d_hot);
-        B200_LAUNCH(ctx, k_msm_merge_hot<F>, 2 * ctx->sm_count, 128, 128 * sizeof(Pt), d_hist, g.T, d_buckets, d_partial, batch_idx > 0 ? 1 : 0, d_hot);
+        B200_LAUNCH(ctx, k_msm_merge_hot<F>, 2 * ctx->sm_count, 128, 128 * sizeof(Pt), d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_hot_list);
         phase_end(ctx);
     }
 
     phase_begin(ctx, PH_MSM_REDUCE);
     B200_LAUNCH(ctx, k_msm_reduce_segments<F>, (total_segs + 127) / 128, 128, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
-    B200_LAUNCH(ctx, k_msm_window_sum<F>, g.nwin, 128, 128 * sizeof(Pt), d_segs, g.nseg, d_win);
+    B200_LAUNCH(ctx, k_msm_window_sum<F>, g.nwin_b, 128, 128 * sizeof(Pt), d_segs, g.nseg, d_win);
     phase_end(ctx);
 
     phase_begin(ctx, PH_MSM_FINAL);
     Pt *h_win = (Pt *)ctx->pinned;
-    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin * sizeof(Pt), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * sizeof(Pt), cudaMemcpyDeviceToHost, st));
     phase_end(ctx);
     B200_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
 
     // Horner over the windows (multiexp.cpp:137-141) on the host's 4x64 field
-    if (sizeof(F) == 32) host_horner_g1(h_win, g.nwin, g.c, out_host);
+    if (g.nwin_b == 1) *out_host = h_win[0];
+    else if (!g2) host_horner_g1(h_win, g.nwin, g.c, out_host);
     else host_horner_g2(h_win, g.nwin, g.c, out_host);
     return B200_OK;
 }

@@ -1,7 +1,14 @@
-// G1 instantiation of the Pippenger pipeline (F = Fq; bases 64 B affine, buckets 128 B XYZZ).
+// G1 instantiation of the Pippenger pipeline (msm.cuh).
 #include "msm.cuh"
 namespace b200 {
-int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G1Xyzz *out_host) {
-    return msm_run_impl<Fq>(ctx, d_bases, d_scalars, scalar_size, n, out_host);
+int msm_table_windows(int c) { return (256 + c) / c; }
+int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G1Xyzz *out_host,
+               const MsmTableRaw *table) {
+    MsmTable<Fq> t;
+    if (table && table->tbl) { t.tbl = (const Affine<Fq> *)table->tbl; t.n = table->n; t.c = table->c; t.nwin = table->nwin; }
+    return msm_run_impl<Fq>(ctx, d_bases, d_scalars, scalar_size, n, out_host, &t);
+}
+int msm_g1_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl) {
+    return msm_precompute_table<Fq>(ctx, (const Affine<Fq> *)d_pts, n, c, (Affine<Fq> *)d_tbl);
 }
 }  // namespace b200

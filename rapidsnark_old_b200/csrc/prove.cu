@@ -29,8 +29,9 @@ struct b200_zkey {
     Range rA, rC, rH;       // this shard's index ranges (A, B1, B2 share rA)
     u32 *d_row_a = nullptr, *d_row_b = nullptr, *d_sig = nullptr;
     Fr *d_coef = nullptr;
-    G1Affine *d_A = nullptr, *d_B1 = nullptr, *d_C = nullptr, *d_H = nullptr;
-    G2Affine *d_B2 = nullptr;
+    G1Affine *d_A = nullptr, *d_B1 = nullptr, *d_C = nullptr, *d_H = nullptr;   // plain shard slices, or
+    G2Affine *d_B2 = nullptr;                                                   // per-window tables (t*.tbl)
+    MsmTableRaw tA, tB1, tB2, tC, tH;
     Fr *d_wtns = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
 };
 
@@ -237,6 +238,45 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     ZK_TRY(upload_slice(c, &zk->d_B2, d->points_b2, zk->rA));
     ZK_TRY(upload_slice(c, &zk->d_C, d->points_c, zk->rC));
     ZK_TRY(upload_slice(c, &zk->d_H, d->points_h, zk->rH));
+    // resident per-window tables (msm.cuh): all windows of an MSM share one bucket set
+    {
+        int pc = c->opt_precomp_c > 0 ? c->opt_precomp_c : 16;
+        int rows = msm_table_windows(pc);
+        uint64_t lenA = zk->rA.hi - zk->rA.lo, lenC = zk->rC.hi - zk->rC.lo, lenH = zk->rH.hi - zk->rH.lo;
+        uint64_t need = (uint64_t)rows * ((2 * lenA + lenC + lenH) * 64 + lenA * 128);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        bool want = c->opt_precomp != 0 && pc >= 11 && pc <= 22 && need < (uint64_t)(free_b * 0.6) &&
+                    (uint64_t)rows * lenH < (1ull << 31) && (uint64_t)rows * lenA < (1ull << 31);
+        if (want) {
+            auto build1 = [&](G1Affine **slice, uint64_t len, MsmTableRaw *t) -> int {
+                if (len == 0) return B200_OK;
+                G1Affine *tbl = nullptr;
+                if (cudaMalloc(&tbl, (size_t)rows * len * sizeof(G1Affine)) != cudaSuccess) { cudaGetLastError(); return B200_OK; }
+                int r = msm_g1_precompute(c, *slice, (u32)len, pc, tbl);
+                if (r != B200_OK) { cudaFree(tbl); return r; }
+                cudaStreamSynchronize(c->stream);
+                cudaFree(*slice);
+                *slice = tbl;                         // row 0 of the table is the original slice
+                t->tbl = tbl; t->n = (u32)len; t->c = pc; t->nwin = rows;
+                return B200_OK;
+            };
+            ZK_TRY(build1(&zk->d_A, lenA, &zk->tA));
+            ZK_TRY(build1(&zk->d_B1, lenA, &zk->tB1));
+            ZK_TRY(build1(&zk->d_C, lenC, &zk->tC));
+            ZK_TRY(build1(&zk->d_H, lenH, &zk->tH));
+            if (lenA) {
+                G2Affine *tbl = nullptr;
+                if (cudaMalloc(&tbl, (size_t)rows * lenA * sizeof(G2Affine)) == cudaSuccess) {
+                    ZK_TRY(msm_g2_precompute(c, zk->d_B2, (u32)lenA, pc, tbl));
+                    cudaStreamSynchronize(c->stream);
+                    cudaFree(zk->d_B2);
+                    zk->d_B2 = tbl;
+                    zk->tB2.tbl = tbl; zk->tB2.n = (u32)lenA; zk->tB2.c = pc; zk->tB2.nwin = rows;
+                } else cudaGetLastError();
+            }
+        }
+    }
     ZK_CUDA(cudaMalloc(&zk->d_wtns, (size_t)d->n_vars * sizeof(Fr)));
     ZK_CUDA(cudaMalloc(&zk->d_a, (size_t)n * sizeof(Fr)));
     ZK_CUDA(cudaMalloc(&zk->d_b, (size_t)n * sizeof(Fr)));
@@ -285,11 +325,11 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     G2Xyzz pib;
     const uint8_t *w = (const uint8_t *)zk->d_wtns;
     // groth16.cpp:173 / :183 / :190 / :197 / :204, restricted to this shard's point range
-    B200_TRY(msm_g1_run(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, &pih));
-    B200_TRY(msm_g1_run(c, zk->d_A, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pia));
-    B200_TRY(msm_g1_run(c, zk->d_B1, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib1));
-    B200_TRY(msm_g2_run(c, zk->d_B2, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib));
-    B200_TRY(msm_g1_run(c, zk->d_C, w + ((size_t)zk->n_public + 1 + zk->rC.lo) * 32, 32, zk->rC.hi - zk->rC.lo, &pic));
+    B200_TRY(msm_g1_run(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, &pih, &zk->tH));
+    B200_TRY(msm_g1_run(c, zk->d_A, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pia, &zk->tA));
+    B200_TRY(msm_g1_run(c, zk->d_B1, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib1, &zk->tB1));
+    B200_TRY(msm_g2_run(c, zk->d_B2, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib, &zk->tB2));
+    B200_TRY(msm_g1_run(c, zk->d_C, w + ((size_t)zk->n_public + 1 + zk->rC.lo) * 32, 32, zk->rC.hi - zk->rC.lo, &pic, &zk->tC));
     B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     phase_collect(c);
     memcpy(o, &pih, 128);

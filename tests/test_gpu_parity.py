@@ -288,3 +288,46 @@ def test_zkey_upload_rejects_bad_records(ctx):
     bad[4 + 4:4 + 8] = (s.n + 5).to_bytes(4, "little")     # row index out of the domain
     with pytest.raises(b200.B200Error):
         ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, bytes(bad), p["A"], p["B1"], p["B2"], p["C"], p["H"])
+
+
+@pytest.mark.parametrize("precomp,pc", [(0, 0), (1, 12), (1, 16), (1, 20)])
+def test_prove_msms_table_variants(ctx, orc, precomp, pc):
+    """resident per-window tables (any window width) and the plain multi-window path give the same points."""
+    s = synth_util.make(10)
+    ctx.set_option("precomp", precomp)
+    ctx.set_option("precomp_c", pc)
+    try:
+        zk = _upload(ctx, s)
+        out = zk.prove_msms(s.wtns_bytes())
+        zk.free()
+    finally:
+        ctx.set_option("precomp", -1)
+        ctx.set_option("precomp_c", 0)
+    assert orc.msms_to_affine(out) == synth_util.expected_affine(orc, s)
+
+
+@pytest.mark.parametrize("acc_smem", [0, 1])
+@pytest.mark.parametrize("g2", [False, True])
+def test_msm_accumulator_variants(ctx, orc, acc_smem, g2):
+    n = 3000
+    ctx.set_option("acc_smem", acc_smem)
+    try:
+        if g2:
+            bases, scalars = _g2_points(orc, 300, 21) * 10, _scalars(n, 22, "skew")
+            got = orc.g2_to_affine(ctx.msm_g2(bases, scalars, n))
+            ref = orc.g2_to_affine(orc.g2_msm(bases, scalars, n))
+        else:
+            bases, scalars = _g1_points(orc, 300, 23) * 10, _scalars(n, 24, "skew")
+            got = orc.g1_to_affine(ctx.msm_g1(bases, scalars, n))
+            ref = orc.g1_to_affine(orc.g1_msm(bases, scalars, n))
+    finally:
+        ctx.set_option("acc_smem", -1)
+    assert got == ref
+
+
+def test_msm_hot_bucket_split(ctx, orc):
+    """one bucket far larger than the task cap: sub-tasks + CTA merge (all scalars equal)."""
+    n = 20000
+    bases = _g1_points(orc, 500, 31) * 40
+    scalars = bn.le32(0x1234) * n
+    assert orc.g1_to_affine(ctx.msm_g1(bases, scalars, n)) == orc.g1_to_affine(orc.g1_msm(bases, scalars, n))

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Tuning harness: one synthetic 2^k circuit, several library configurations, per-phase device times.
+  python tools/prove_bench.py --log-n 20 --configs precomp=0 precomp_c=14 precomp_c=16,acc_smem=0
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import rapidsnark_old_b200 as b200
+import bench
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--configs", nargs="*", default=[""])
+    args = ap.parse_args()
+    ctx = b200.Context(0)
+    s = bench.build_inputs(args.log_n, 2, *bench.gpu_point_makers(ctx))
+    p = s.points
+    wt = s.wtns_bytes()
+    wt_dev = torch.frombuffer(bytearray(wt), dtype=torch.uint8).cuda()
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    coefs = s.coefs_section()
+    for cfg in args.configs:
+        opts = dict(kv.split("=") for kv in cfg.split(",") if kv)
+        for k in ("precomp", "precomp_c", "acc_smem", "msm_window"):
+            ctx.set_option(k, int(opts.get(k, -1 if k in ("precomp", "acc_smem") else 0)))
+        t0 = time.time()
+        zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"])
+        up = time.time() - t0
+        for _ in range(2):
+            zk.prove_msms_dev(wt_dev.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ph = {}
+        e0.record(stream)
+        for _ in range(args.iters):
+            zk.prove_msms_dev(wt_dev.data_ptr())
+            for k, v in ctx.phase_ms().items():
+                ph[k] = ph.get(k, 0.0) + v / args.iters
+        e1.record(stream)
+        torch.cuda.synchronize()
+        print(json.dumps({"config": cfg or "default", "ms": round(e0.elapsed_time(e1) / args.iters, 3),
+                          "upload_s": round(up, 2), "phases": {k: round(v, 3) for k, v in ph.items() if v > 0},
+                          "free_gb": round(torch.cuda.mem_get_info()[0] / 2**30, 1)}), flush=True)
+        zk.free()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
