@@ -33,6 +33,11 @@ int b200_init(int device, b200_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->c.side, cudaStreamNonBlocking);
+    for (int i = 0; i < Ctx::MSM_SLOTS && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&h->c.ev_acc[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_done[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { g_init_err = cudaGetErrorString(e); delete h; return B200_ERR_CUDA; }
     *out = h;
     return B200_OK;
@@ -43,12 +48,16 @@ void b200_free(b200_ctx *h) {
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *all[] = {&c->w_hist, &c->w_cursor, &c->w_entries, &c->w_buckets, &c->w_partial, &c->w_hot,
-                     &c->w_scan_totals, &c->w_segs, &c->w_win, &c->w_plan, &c->w_tasks, &c->w_in_bases, &c->w_in_scalars, &c->w_ntt};
+    if (c->side) cudaStreamSynchronize(c->side);
+    DevBuf *all[] = {&c->w_hist, &c->w_cursor, &c->w_entries, &c->w_buckets[0], &c->w_buckets[1], &c->w_partial, &c->w_hot,
+                     &c->w_scan_totals, &c->w_segs[0], &c->w_segs[1], &c->w_win, &c->w_plan, &c->w_tasks, &c->w_in_bases,
+                     &c->w_in_scalars, &c->w_ntt};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t ev : c->evpool) cudaEventDestroy(ev);
     ntt_free_tables(c);
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) { if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
+    if (c->side) cudaStreamDestroy(c->side);
     cudaStreamDestroy(c->stream);
     delete h;
 }

@@ -32,6 +32,11 @@ struct DevBuf {
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;       // bucket reduction of MSM k runs here while MSM k+1 accumulates on `stream`
+    static const int MSM_SLOTS = 8;    // in-flight MSM results
+    cudaEvent_t ev_acc[MSM_SLOTS] = {nullptr}, ev_done[MSM_SLOTS] = {nullptr};
+    int bucket_buf_slot[2] = {-1, -1}; // which result slot last used each of the two bucket buffers
+    int next_bucket_buf = 0;
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -47,11 +52,13 @@ struct Ctx {
     std::vector<DevBuf *> bufs;  // everything to free
 
     // MSM workspaces (shared by G1/G2 calls; grow-only)
-    DevBuf w_hist, w_cursor, w_entries, w_buckets, w_partial, w_hot, w_scan_totals, w_segs, w_win, w_plan, w_tasks;
+    DevBuf w_hist, w_cursor, w_entries, w_buckets[2], w_partial, w_hot, w_scan_totals, w_segs[2], w_win, w_plan, w_tasks;
     DevBuf w_in_bases, w_in_scalars;   // staging for host-pointer calls
     DevBuf w_ntt;                      // staging for host-pointer NTT calls
     void *pinned = nullptr;            // small pinned host buffer for results
     size_t pinned_cap = 0;
+
+    struct SlotInfo { int nwin_b = 0, nwin = 0, c = 0; bool used = false; } slot_info[MSM_SLOTS];
 
     // NTT twiddle tables (built lazily per log-size)
     struct Twiddles;
@@ -80,6 +87,7 @@ inline int ctx_reserve(Ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return B200_OK;
     if (b.p) {
         B200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->side) B200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->side));
         B200_CUDA_CHECK(ctx, cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -101,13 +109,13 @@ inline int ctx_pinned(Ctx *ctx, size_t bytes) {
 }
 
 // phase timers: CUDA events on the ctx stream around each phase; collected after the final sync
-inline int phase_event(Ctx *ctx) {
+inline int phase_event(Ctx *ctx, cudaStream_t st) {
     if (ctx->ev_used == (int)ctx->evpool.size()) {
         cudaEvent_t e;
         cudaEventCreate(&e);
         ctx->evpool.push_back(e);
     }
-    cudaEventRecord(ctx->evpool[ctx->ev_used], ctx->stream);
+    cudaEventRecord(ctx->evpool[ctx->ev_used], st);
     return ctx->ev_used++;
 }
 inline void phase_reset(Ctx *ctx) {
@@ -115,14 +123,14 @@ inline void phase_reset(Ctx *ctx) {
     ctx->segs.clear();
     for (int i = 0; i < PH_COUNT; i++) ctx->phase_ms[i] = 0.f;
 }
-inline void phase_begin(Ctx *ctx, Phase ph) {
+inline void phase_begin(Ctx *ctx, Phase ph, cudaStream_t st = nullptr) {
     Ctx::Seg s;
     s.ph = ph;
-    s.e0 = phase_event(ctx);
+    s.e0 = phase_event(ctx, st ? st : ctx->stream);
     s.e1 = -1;
     ctx->segs.push_back(s);
 }
-inline void phase_end(Ctx *ctx) { ctx->segs.back().e1 = phase_event(ctx); }
+inline void phase_end(Ctx *ctx, cudaStream_t st = nullptr) { ctx->segs.back().e1 = phase_event(ctx, st ? st : ctx->stream); }
 inline void phase_collect(Ctx *ctx) {  // stream must be synchronized
     for (auto &s : ctx->segs) {
         if (s.e1 < 0) continue;
@@ -134,9 +142,10 @@ inline void phase_collect(Ctx *ctx) {  // stream must be synchronized
 }
 
 // launch bookkeeping: every kernel launch of ours goes through this macro
-#define B200_LAUNCH(ctx, kernel, grid, block, smem, ...)                            \
+#define B200_LAUNCH(ctx, kernel, grid, block, smem, ...) B200_LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)
+#define B200_LAUNCH_ON(ctx, st_, kernel, grid, block, smem, ...)                    \
     do {                                                                            \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+        kernel<<<(grid), (block), (smem), (st_)>>>(__VA_ARGS__);                    \
         (ctx)->launches++;                                                          \
         cudaError_t e__ = cudaGetLastError();                                       \
         if (e__ != cudaSuccess) {                                                   \
@@ -163,6 +172,13 @@ int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t sc
                const MsmTableRaw *table = nullptr);
 int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G2Xyzz *out_host,
                const MsmTableRaw *table = nullptr);
+// asynchronous pair: enqueue all kernels of one MSM (result lands in pinned slot `slot`), collect = wait + host Horner
+int msm_g1_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
+                   const MsmTableRaw *table = nullptr, bool reuse_sort = false);
+int msm_g2_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
+                   const MsmTableRaw *table = nullptr, bool reuse_sort = false);
+int msm_g1_collect(Ctx *ctx, int slot, G1Xyzz *out_host);
+int msm_g2_collect(Ctx *ctx, int slot, G2Xyzz *out_host);
 int msm_g1_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl);
 int msm_g2_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl);
 

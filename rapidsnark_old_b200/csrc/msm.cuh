@@ -53,6 +53,8 @@ struct MsmGeom {
 
 static const u32 MSM_MAX_BATCH = 1u << 24;   // points per sort batch (entries < 2^32, entry index < 2^31)
 static const int MSM_MAX_WIN = 65;
+static const u32 MSM_TARGET_TASKS = 1u << 18;
+static const u32 MSM_WARM_MAX = 64;          // buckets cut into <= 64 tasks are folded by one thread, more by a CTA
 static const u32 MSM_MAX_CAP = 2048;         // task-length histogram has MSM_MAX_CAP + 1 <= 4096 bins
 
 inline int msm_auto_c(uint64_t n) {
@@ -72,9 +74,13 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     g.nbk = 1u << (c - 1);
     g.nwin_b = shared_buckets ? 1u : (u32)g.nwin;
     g.NB = g.nwin_b * g.nbk;
-    uint64_t avg = n_batch * (uint64_t)g.nwin / g.NB + 1;
-    u32 cap = 256;
-    while (cap < 4 * avg && cap < MSM_MAX_CAP) cap <<= 1;
+    // task cap: with plenty of buckets (>= 2^18) a task is a whole bucket unless it is 4x the average;
+    // with few, large buckets they are cut so that about MSM_TARGET_TASKS tasks exist (load balance)
+    uint64_t ent = n_batch * (uint64_t)g.nwin;
+    uint64_t avg = ent / g.NB + 1;
+    u32 cap = 32;
+    if ((ent < g.NB ? ent : g.NB) >= (1u << 18)) { while (cap < 4 * avg && cap < MSM_MAX_CAP) cap <<= 1; }
+    else { while ((uint64_t)cap * 2 * MSM_TARGET_TASKS <= ent && cap < MSM_MAX_CAP) cap <<= 1; }
     g.CAP = cap;
     g.L = g.nbk >= 16 ? 16 : g.nbk;
     g.nseg = g.nbk / g.L;
@@ -220,11 +226,12 @@ static __global__ void __launch_bounds__(1024) k_scan_add(u32 *__restrict__ data
 // ------------------------------------------------------------------------------------------------
 // 4: task plan - buckets (or CAP-sized pieces of big buckets) sorted by length, longest first
 // ------------------------------------------------------------------------------------------------
-// plan[0] = hot partial slots allocated, plan[1] = number of hot buckets
+// plan[0] = partial slots allocated, plan[1] = hot buckets (> MSM_WARM_MAX tasks), plan[2] = tasks,
+// plan[3] = warm buckets (2..MSM_WARM_MAX tasks)
 static __global__ void __launch_bounds__(256) k_msm_plan_count(const u32 *__restrict__ off, u32 NB, u32 CAP,
                                                           u32 *__restrict__ lenhist /* [4096], index CAP_MAX - len */,
                                                           u32 *__restrict__ plan, u32 *__restrict__ hot_base,
-                                                          u32 *__restrict__ hot_list) {
+                                                          u32 *__restrict__ hot_list, u32 *__restrict__ warm_list) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= NB) return;
     u32 cnt = off[b + 1] - off[b];
@@ -235,7 +242,8 @@ static __global__ void __launch_bounds__(256) k_msm_plan_count(const u32 *__rest
     u32 ntask = nfull + (rem ? 1u : 0u);
     if (ntask > 1) {
         hot_base[b] = atomicAdd(&plan[0], ntask);
-        hot_list[atomicAdd(&plan[1], 1u)] = b;
+        if (ntask > MSM_WARM_MAX) hot_list[atomicAdd(&plan[1], 1u)] = b;
+        else warm_list[atomicAdd(&plan[3], 1u)] = b;
     }
 }
 
@@ -344,6 +352,28 @@ DEVFN void cta_tree_sum(Xyzz<F> &acc, Xyzz<F> *sm) {
             ec_add(acc, q);
         }
         __syncthreads();
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_merge_warm(const u32 *__restrict__ off, u32 CAP,
+                                                          Xyzz<F> *__restrict__ buckets,
+                                                          const Xyzz<F> *__restrict__ partial, int add_existing,
+                                                          const u32 *__restrict__ plan, const u32 *__restrict__ hot_base,
+                                                          const u32 *__restrict__ warm_list) {
+    const u32 nwarm = plan[3];
+    for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h < nwarm; h += gridDim.x * blockDim.x) {
+        const u32 b = warm_list[h];
+        const u32 cnt = off[b + 1] - off[b];
+        const u32 ntask = (cnt + CAP - 1) / CAP;
+        const Xyzz<F> *src = partial + hot_base[b];
+        Xyzz<F> acc = ld_struct(src);
+        for (u32 j = 1; j < ntask; j++) {
+            Xyzz<F> q = ld_struct(src + j);
+            ec_add(acc, q);
+        }
+        if (add_existing) { Xyzz<F> old = ld_struct(buckets + b); ec_add(acc, old); }
+        st_struct(buckets + b, acc);
     }
 }
 
@@ -473,11 +503,13 @@ int msm_precompute_table(Ctx *ctx, const Affine<F> *d_pts, u32 n, int c, Affine<
 }
 
 template <class F>
-int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint32_t scalar_size, uint64_t n,
-                 Xyzz<F> *out_host, const MsmTable<F> *table = nullptr) {
+int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint32_t scalar_size, uint64_t n, int slot,
+                     const MsmTable<F> *table, bool reuse_sort) {
     typedef Xyzz<F> Pt;
-    *out_host = Pt::zero();
-    if (n == 0) return B200_OK;
+    if (slot < 0 || slot >= Ctx::MSM_SLOTS) { ctx->err = "msm: bad result slot"; return B200_ERR_ARG; }
+    Ctx::SlotInfo &si = ctx->slot_info[slot];
+    si.used = false;
+    if (n == 0) { si.nwin_b = 0; si.used = true; return B200_OK; }
     if (scalar_size == 0 || scalar_size > 32) { ctx->err = "msm: scalar_size must be 1..32 bytes"; return B200_ERR_ARG; }
     if (!d_bases_v || !d_scalars_v) { ctx->err = "msm: null input"; return B200_ERR_ARG; }
     const bool pre = table && table->tbl;
@@ -491,39 +523,48 @@ int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint3
     MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre);
     if (g.nwin > MSM_MAX_WIN) { ctx->err = "msm: too many windows"; return B200_ERR_ARG; }
     if (pre && (uint64_t)g.nwin * n >= (1ull << 31)) { ctx->err = "msm: table too large for 31-bit entries"; return B200_ERR_ARG; }
+    if (reuse_sort && (n > batch_max)) { ctx->err = "msm: reuse_sort needs a single batch"; return B200_ERR_ARG; }
     const size_t hist_len = ((size_t)g.NB + 1 + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
     const u32 ntiles = (u32)(hist_len / SCAN_TILE);
     const size_t max_entries = (size_t)batch_max * g.nwin;
     const size_t max_tasks = (max_entries < g.NB ? max_entries : g.NB) + max_entries / g.CAP + 1;
     const size_t max_partials = 2 * (max_entries / g.CAP) + 2;
     const u32 total_segs = g.nwin_b * g.nseg;
+    const size_t PT_MAX = sizeof(G2Xyzz);   // G1 and G2 calls share the buffers: size for the larger point
 
+    const int bb = ctx->next_bucket_buf;
+    ctx->next_bucket_buf ^= 1;
     B200_TRY(ctx_reserve(ctx, ctx->w_hist, hist_len * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_cursor, hist_len * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_scan_totals, (size_t)ntiles * 4 + 16));
     B200_TRY(ctx_reserve(ctx, ctx->w_entries, max_entries * 4 + 16));
-    B200_TRY(ctx_reserve(ctx, ctx->w_buckets, (size_t)g.NB * sizeof(Pt)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_partial, max_partials * sizeof(Pt)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_hot, ((size_t)2 * g.NB + 8) * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_buckets[bb], (size_t)g.NB * PT_MAX));
+    B200_TRY(ctx_reserve(ctx, ctx->w_partial, max_partials * PT_MAX));
+    B200_TRY(ctx_reserve(ctx, ctx->w_hot, ((size_t)3 * g.NB + 8) * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_plan, (size_t)(2 * SCAN_TILE + 16) * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_tasks, max_tasks * sizeof(uint2)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_segs, (size_t)total_segs * sizeof(Pt)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_win, (size_t)MSM_MAX_WIN * sizeof(Pt)));
-    B200_TRY(ctx_pinned(ctx, (size_t)MSM_MAX_WIN * sizeof(G2Xyzz)));
+    B200_TRY(ctx_reserve(ctx, ctx->w_segs[bb], (size_t)total_segs * PT_MAX));
+    B200_TRY(ctx_reserve(ctx, ctx->w_win, (size_t)Ctx::MSM_SLOTS * MSM_MAX_WIN * PT_MAX));
+    B200_TRY(ctx_pinned(ctx, (size_t)Ctx::MSM_SLOTS * MSM_MAX_WIN * PT_MAX));
 
     u32 *d_hist = (u32 *)ctx->w_hist.p, *d_cursor = (u32 *)ctx->w_cursor.p, *d_totals = (u32 *)ctx->w_scan_totals.p;
     u32 *d_entries = (u32 *)ctx->w_entries.p;
-    u32 *d_hot_base = (u32 *)ctx->w_hot.p, *d_hot_list = d_hot_base + g.NB;
+    u32 *d_hot_base = (u32 *)ctx->w_hot.p, *d_hot_list = d_hot_base + g.NB, *d_warm_list = d_hot_list + g.NB;
     // plan buffer: [0..4095] task-length histogram (then its scan), [4096..8191] scan cursors, [8192..] counters
     u32 *d_lenhist = (u32 *)ctx->w_plan.p, *d_lencur = d_lenhist + SCAN_TILE, *d_plan = d_lenhist + 2 * SCAN_TILE;
     uint2 *d_tasks = (uint2 *)ctx->w_tasks.p;
-    Pt *d_buckets = (Pt *)ctx->w_buckets.p, *d_partial = (Pt *)ctx->w_partial.p;
-    Pt *d_segs = (Pt *)ctx->w_segs.p, *d_win = (Pt *)ctx->w_win.p;
-    cudaStream_t st = ctx->stream;
+    Pt *d_buckets = (Pt *)ctx->w_buckets[bb].p, *d_partial = (Pt *)ctx->w_partial.p;
+    Pt *d_segs = (Pt *)ctx->w_segs[bb].p;
+    Pt *d_win = (Pt *)((uint8_t *)ctx->w_win.p + (size_t)slot * MSM_MAX_WIN * PT_MAX);
+    Pt *h_win = (Pt *)((uint8_t *)ctx->pinned + (size_t)slot * MSM_MAX_WIN * PT_MAX);
+    cudaStream_t st = ctx->stream, side = ctx->side;
     const bool g2 = sizeof(F) != 32;
-    const bool acc_smem = ctx->opt_acc_smem >= 0 ? (ctx->opt_acc_smem != 0) : g2;   // default: G2 only
+    const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
     const size_t acc_smem_bytes = 128 * sizeof(Pt);
 
+    // this bucket buffer may still be read by the side-stream reduction of an earlier MSM
+    if (ctx->bucket_buf_slot[bb] >= 0) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_done[ctx->bucket_buf_slot[bb]], 0));
+    ctx->bucket_buf_slot[bb] = slot;
     B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_buckets, 0, (size_t)g.NB * sizeof(Pt), st));
 
     int batch_idx = 0;
@@ -535,27 +576,29 @@ int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint3
         const u32 tstride = pre ? table->n : 0;
         const int add_existing = batch_idx > 0 ? 1 : 0;
 
-        phase_begin(ctx, PH_MSM_SORT);
-        B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_hist, 0, hist_len * 4, st));
-        B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_lenhist, 0, (size_t)(2 * SCAN_TILE + 16) * 4, st));
-        B200_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_hist, (u32 *)nullptr);
-        B200_LAUNCH(ctx, k_scan_tile, ntiles, 1024, 0, d_hist, d_totals);
-        B200_LAUNCH(ctx, k_scan_totals, 1, 1024, 0, d_totals, ntiles);
-        B200_LAUNCH(ctx, k_scan_add, ntiles, 1024, 0, d_hist, d_totals, d_cursor);
-        B200_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_cursor, d_entries);
-        // task plan: histogram of task lengths (descending), scan, placement
-        B200_LAUNCH(ctx, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list);
-        B200_LAUNCH(ctx, k_scan_tile, 1, 1024, 0, d_lenhist, d_plan + 2);      // d_plan[2] = number of tasks
-        B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, st));
-        B200_LAUNCH(ctx, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
-        phase_end(ctx);
+        if (!reuse_sort) {
+            phase_begin(ctx, PH_MSM_SORT);
+            B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_hist, 0, hist_len * 4, st));
+            B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_lenhist, 0, (size_t)(2 * SCAN_TILE + 16) * 4, st));
+            B200_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_hist, (u32 *)nullptr);
+            B200_LAUNCH(ctx, k_scan_tile, ntiles, 1024, 0, d_hist, d_totals);
+            B200_LAUNCH(ctx, k_scan_totals, 1, 1024, 0, d_totals, ntiles);
+            B200_LAUNCH(ctx, k_scan_add, ntiles, 1024, 0, d_hist, d_totals, d_cursor);
+            B200_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_cursor, d_entries);
+            // task plan: histogram of task lengths (descending), scan, placement
+            B200_LAUNCH(ctx, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list, d_warm_list);
+            B200_LAUNCH(ctx, k_scan_tile, 1, 1024, 0, d_lenhist, d_plan + 2);      // d_plan[2] = number of tasks
+            B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, st));
+            B200_LAUNCH(ctx, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
+            phase_end(ctx);
+        }
 
         phase_begin(ctx, g2 ? PH_MSM_ACCUM_G2 : PH_MSM_ACCUM);
         const size_t ent = (size_t)nb * g.nwin;
         const size_t tasks_ub = (ent < g.NB ? ent : g.NB) + ent / g.CAP + 1;
         const u32 agrid = (u32)((tasks_ub + 127) / 128);
         {
-            // variants: running sum in registers (G1 default) or in shared memory (G2 default: 64-register sum)
+            // variants: running sum in registers (default) or in shared memory
             void (*kacc)(const Affine<F> *, const u32 *, const u32 *, const uint2 *, const u32 *, u32, const u32 *, Pt *, Pt *, int);
             size_t smem = 0;
             if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
@@ -565,25 +608,37 @@ int msm_run_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint3
         phase_end(ctx);
 
         phase_begin(ctx, PH_MSM_MERGE);
+        B200_LAUNCH(ctx, k_msm_merge_warm<F>, 4 * ctx->sm_count, 128, 0, d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_warm_list);
         B200_LAUNCH(ctx, k_msm_merge_hot<F>, 2 * ctx->sm_count, 128, 128 * sizeof(Pt), d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_hot_list);
         phase_end(ctx);
     }
 
-    phase_begin(ctx, PH_MSM_REDUCE);
-    B200_LAUNCH(ctx, k_msm_reduce_segments<F>, (total_segs + 127) / 128, 128, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
-    B200_LAUNCH(ctx, k_msm_window_sum<F>, g.nwin_b, 128, 128 * sizeof(Pt), d_segs, g.nseg, d_win);
-    phase_end(ctx);
+    // bucket reduction + window sums + D2H on the side stream: overlaps the next MSM's sort / accumulation
+    B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_acc[slot], st));
+    B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(side, ctx->ev_acc[slot], 0));
+    phase_begin(ctx, PH_MSM_REDUCE, side);
+    B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 127) / 128, 128, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
+    B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, g.nwin_b, 128, 128 * sizeof(Pt), d_segs, g.nseg, d_win);
+    phase_end(ctx, side);
+    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * sizeof(Pt), cudaMemcpyDeviceToHost, side));
+    B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_done[slot], side));
+    si.nwin_b = (int)g.nwin_b; si.nwin = g.nwin; si.c = g.c; si.used = true;
+    return B200_OK;
+}
 
-    phase_begin(ctx, PH_MSM_FINAL);
-    Pt *h_win = (Pt *)ctx->pinned;
-    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * sizeof(Pt), cudaMemcpyDeviceToHost, st));
-    phase_end(ctx);
-    B200_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-
+template <class F>
+int msm_collect_impl(Ctx *ctx, int slot, Xyzz<F> *out_host) {
+    typedef Xyzz<F> Pt;
+    if (slot < 0 || slot >= Ctx::MSM_SLOTS || !ctx->slot_info[slot].used) { ctx->err = "msm: nothing enqueued in this slot"; return B200_ERR_ARG; }
+    Ctx::SlotInfo &si = ctx->slot_info[slot];
+    si.used = false;
+    if (si.nwin_b == 0) { *out_host = Pt::zero(); return B200_OK; }
+    B200_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev_done[slot]));
+    const Pt *h_win = (const Pt *)((const uint8_t *)ctx->pinned + (size_t)slot * MSM_MAX_WIN * sizeof(G2Xyzz));
     // Horner over the windows (multiexp.cpp:137-141) on the host's 4x64 field
-    if (g.nwin_b == 1) *out_host = h_win[0];
-    else if (!g2) host_horner_g1(h_win, g.nwin, g.c, out_host);
-    else host_horner_g2(h_win, g.nwin, g.c, out_host);
+    if (si.nwin_b == 1) *out_host = h_win[0];
+    else if (sizeof(F) == 32) host_horner_g1(h_win, si.nwin, si.c, out_host);
+    else host_horner_g2(h_win, si.nwin, si.c, out_host);
     return B200_OK;
 }
 

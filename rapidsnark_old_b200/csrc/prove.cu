@@ -219,7 +219,7 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     zk->ctx = c;
     zk->n_vars = d->n_vars; zk->n_public = d->n_public; zk->domain_size = n; zk->n_coefs = d->n_coefs;
     zk->rA = shard_range(d->n_vars, d->shard_index, cnt);
-    zk->rC = shard_range(d->n_vars - d->n_public - 1, d->shard_index, cnt);
+    zk->rC = zk->rA;   // the C table is padded to the witness indexing (see below)
     zk->rH = shard_range(n, d->shard_index, cnt);
     int rc = B200_OK;
     auto fail = [&](int code) { b200_zkey_free(zk); return code; };
@@ -236,13 +236,22 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     ZK_TRY(upload_slice(c, &zk->d_A, d->points_a, zk->rA));
     ZK_TRY(upload_slice(c, &zk->d_B1, d->points_b1, zk->rA));
     ZK_TRY(upload_slice(c, &zk->d_B2, d->points_b2, zk->rA));
-    ZK_TRY(upload_slice(c, &zk->d_C, d->points_c, zk->rC));
+    {   // C is stored aligned with the witness: (n_public + 1) leading points at infinity, so the A, B1, B2 and C
+        // MSMs all read the same scalars and can share one digit sort (zero bases are skipped by the mixed add)
+        const uint64_t lo = zk->rA.lo, hi = zk->rA.hi, skip = (uint64_t)d->n_public + 1;
+        ZK_CUDA(cudaMalloc((void **)&zk->d_C, std::max<size_t>(hi - lo, 1) * sizeof(G1Affine)));
+        ZK_CUDA(cudaMemsetAsync(zk->d_C, 0, std::max<size_t>(hi - lo, 1) * sizeof(G1Affine), c->stream));
+        const uint64_t from = std::max(lo, skip);
+        if (hi > from)
+            ZK_CUDA(cudaMemcpyAsync(zk->d_C + (from - lo), (const uint8_t *)d->points_c + (from - skip) * sizeof(G1Affine),
+                                    (hi - from) * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
+    }
     ZK_TRY(upload_slice(c, &zk->d_H, d->points_h, zk->rH));
     // resident per-window tables (msm.cuh): all windows of an MSM share one bucket set
     {
         int pc = c->opt_precomp_c > 0 ? c->opt_precomp_c : 16;
         int rows = msm_table_windows(pc);
-        uint64_t lenA = zk->rA.hi - zk->rA.lo, lenC = zk->rC.hi - zk->rC.lo, lenH = zk->rH.hi - zk->rH.lo;
+        uint64_t lenA = zk->rA.hi - zk->rA.lo, lenC = lenA, lenH = zk->rH.hi - zk->rH.lo;
         uint64_t need = (uint64_t)rows * ((2 * lenA + lenC + lenH) * 64 + lenA * 128);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -324,13 +333,24 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     G1Xyzz pih, pia, pib1, pic;
     G2Xyzz pib;
     const uint8_t *w = (const uint8_t *)zk->d_wtns;
-    // groth16.cpp:173 / :183 / :190 / :197 / :204, restricted to this shard's point range
-    B200_TRY(msm_g1_run(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, &pih, &zk->tH));
-    B200_TRY(msm_g1_run(c, zk->d_A, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pia, &zk->tA));
-    B200_TRY(msm_g1_run(c, zk->d_B1, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib1, &zk->tB1));
-    B200_TRY(msm_g2_run(c, zk->d_B2, w + zk->rA.lo * 32, 32, zk->rA.hi - zk->rA.lo, &pib, &zk->tB2));
-    B200_TRY(msm_g1_run(c, zk->d_C, w + ((size_t)zk->n_public + 1 + zk->rC.lo) * 32, 32, zk->rC.hi - zk->rC.lo, &pic, &zk->tC));
+    // groth16.cpp:173 / :183 / :190 / :197 / :204, restricted to this shard's point range.  All five MSMs are
+    // enqueued back to back (bucket reductions overlap the next accumulation on a side stream), then collected.
+    // The four witness MSMs read the same scalars with the same geometry: sorted once, reused three times.
+    const uint64_t lenA = zk->rA.hi - zk->rA.lo;
+    const bool same_geom = (!zk->tA.tbl == !zk->tB1.tbl) && (!zk->tA.tbl == !zk->tB2.tbl) && (!zk->tA.tbl == !zk->tC.tbl) &&
+                           lenA <= (1u << 24);
+    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH));
+    B200_TRY(msm_g2_enqueue(c, zk->d_B2, w + zk->rA.lo * 32, 32, lenA, 1, &zk->tB2));
+    B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom));
+    B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom));
+    B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom));
+    B200_TRY(msm_g1_collect(c, 0, &pih));
+    B200_TRY(msm_g2_collect(c, 1, &pib));
+    B200_TRY(msm_g1_collect(c, 2, &pia));
+    B200_TRY(msm_g1_collect(c, 3, &pib1));
+    B200_TRY(msm_g1_collect(c, 4, &pic));
     B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->side));
     phase_collect(c);
     memcpy(o, &pih, 128);
     memcpy(o + 128, &pia, 128);
