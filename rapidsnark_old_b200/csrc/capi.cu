@@ -33,10 +33,18 @@ int b200_init(int device, b200_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->c.side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->c.hstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_h, cudaEventDisableTiming);
+    if (e == cudaSuccess) {   // side stream (bucket folding / reduction): highest priority so its few CTAs are not starved
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        for (int i = 0; i < Ctx::MSM_SLOTS && e == cudaSuccess; i++)
+            e = cudaStreamCreateWithPriority(&h->c.side[i], cudaStreamNonBlocking, hi_p);
+    }
     for (int i = 0; i < Ctx::MSM_SLOTS && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&h->c.ev_acc[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_merge[i], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) { g_init_err = cudaGetErrorString(e); delete h; return B200_ERR_CUDA; }
     *out = h;
@@ -48,16 +56,22 @@ void b200_free(b200_ctx *h) {
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->side) cudaStreamSynchronize(c->side);
-    DevBuf *all[] = {&c->w_hist, &c->w_cursor, &c->w_entries, &c->w_buckets[0], &c->w_buckets[1], &c->w_partial, &c->w_hot,
-                     &c->w_scan_totals, &c->w_segs[0], &c->w_segs[1], &c->w_win, &c->w_plan, &c->w_tasks, &c->w_in_bases,
-                     &c->w_in_scalars, &c->w_ntt};
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) cudaStreamSynchronize(c->side[i]);
+    DevBuf *all[] = {&c->w_hist, &c->w_cursor, &c->w_entries, &c->w_hot, &c->w_scan_totals, &c->w_win, &c->w_plan,
+                     &c->w_tasks, &c->w_in_bases, &c->w_in_scalars, &c->w_ntt};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) {
+        if (c->w_buckets[i].p) cudaFree(c->w_buckets[i].p);
+        if (c->w_partial[i].p) cudaFree(c->w_partial[i].p);
+        if (c->w_segs[i].p) cudaFree(c->w_segs[i].p);
+    }
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t ev : c->evpool) cudaEventDestroy(ev);
     ntt_free_tables(c);
-    for (int i = 0; i < Ctx::MSM_SLOTS; i++) { if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
-    if (c->side) cudaStreamDestroy(c->side);
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) { if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_merge[i]) cudaEventDestroy(c->ev_merge[i]); }
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    if (c->hstream) cudaStreamDestroy(c->hstream);
+    if (c->ev_h) cudaEventDestroy(c->ev_h);
     cudaStreamDestroy(c->stream);
     delete h;
 }
@@ -72,6 +86,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "acc_smem")) h->c.opt_acc_smem = value;
     else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;
     else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;
+    else if (!strcmp(name, "target_tasks_log2")) h->c.opt_target_tasks_log2 = value;
     else { h->c.err = std::string("unknown option ") + name; return B200_ERR_ARG; }
     return B200_OK;
 }

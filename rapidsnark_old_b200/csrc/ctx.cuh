@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -32,11 +33,14 @@ struct DevBuf {
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;       // bucket reduction of MSM k runs here while MSM k+1 accumulates on `stream`
-    static const int MSM_SLOTS = 8;    // in-flight MSM results
-    cudaEvent_t ev_acc[MSM_SLOTS] = {nullptr}, ev_done[MSM_SLOTS] = {nullptr};
-    int bucket_buf_slot[2] = {-1, -1}; // which result slot last used each of the two bucket buffers
-    int next_bucket_buf = 0;
+    cudaStream_t hstream = nullptr;    // H pipeline (a,b,c build + NTTs) overlapping the witness MSMs
+    cudaEvent_t ev_h = nullptr;
+    static const int MSM_SLOTS = 8;    // in-flight MSM results; each slot owns a side stream and its bucket buffers
+    cudaStream_t side[MSM_SLOTS] = {nullptr};   // folding + reduction of slot k's MSM run here (high priority) while
+                                                // the next MSMs sort / accumulate on `stream`
+    cudaEvent_t ev_acc[MSM_SLOTS] = {nullptr}, ev_done[MSM_SLOTS] = {nullptr}, ev_merge[MSM_SLOTS] = {nullptr};
+    bool slot_busy[MSM_SLOTS] = {false};        // ev_done[slot] recorded and not yet waited for
+    unsigned sort_readers = 0;                  // slots whose side-stream merge reads the current sort workspace
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -52,7 +56,8 @@ struct Ctx {
     std::vector<DevBuf *> bufs;  // everything to free
 
     // MSM workspaces (shared by G1/G2 calls; grow-only)
-    DevBuf w_hist, w_cursor, w_entries, w_buckets[2], w_partial, w_hot, w_scan_totals, w_segs[2], w_win, w_plan, w_tasks;
+    DevBuf w_hist, w_cursor, w_entries, w_buckets[MSM_SLOTS], w_partial[MSM_SLOTS], w_hot, w_scan_totals, w_segs[MSM_SLOTS], w_win, w_plan, w_tasks;
+    int opt_target_tasks_log2 = 0;     // 0 = default (msm.cuh)
     DevBuf w_in_bases, w_in_scalars;   // staging for host-pointer calls
     DevBuf w_ntt;                      // staging for host-pointer NTT calls
     void *pinned = nullptr;            // small pinned host buffer for results
@@ -87,7 +92,7 @@ inline int ctx_reserve(Ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return B200_OK;
     if (b.p) {
         B200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->side) B200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->side));
+        for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (ctx->side[i]) B200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->side[i]));
         B200_CUDA_CHECK(ctx, cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -131,11 +136,18 @@ inline void phase_begin(Ctx *ctx, Phase ph, cudaStream_t st = nullptr) {
     ctx->segs.push_back(s);
 }
 inline void phase_end(Ctx *ctx, cudaStream_t st = nullptr) { ctx->segs.back().e1 = phase_event(ctx, st ? st : ctx->stream); }
-inline void phase_collect(Ctx *ctx) {  // stream must be synchronized
+inline void phase_collect(Ctx *ctx) {  // both streams must be synchronized
+    static const bool timeline = getenv("B200_TIMELINE") != nullptr;
     for (auto &s : ctx->segs) {
         if (s.e1 < 0) continue;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->evpool[s.e0], ctx->evpool[s.e1]) == cudaSuccess) ctx->phase_ms[s.ph] += ms;
+        if (timeline && !ctx->segs.empty()) {
+            float t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&t0, ctx->evpool[ctx->segs[0].e0], ctx->evpool[s.e0]);
+            cudaEventElapsedTime(&t1, ctx->evpool[ctx->segs[0].e0], ctx->evpool[s.e1]);
+            fprintf(stderr, "[timeline] phase %d  %8.3f -> %8.3f ms\n", s.ph, t0, t1);
+        }
     }
     ctx->segs.clear();
     ctx->ev_used = 0;

@@ -44,13 +44,13 @@ template <class F>
 HD_COLD Xyzz<F> ec_dbl_affine(const Affine<F> &p) {
     Xyzz<F> r;
     F u = fdbl(p.y);
-    F v = fsqr(u);
-    F w = fmul(u, v);
-    F s = fmul(p.x, v);
-    F xx = fsqr(p.x);
+    F v = csqr(u);
+    F w = cmul(u, v);
+    F s = cmul(p.x, v);
+    F xx = csqr(p.x);
     F m = fadd(fdbl(xx), xx);
-    r.x = fsub(fsqr(m), fdbl(s));
-    r.y = fsub(fmul(m, fsub(s, r.x)), fmul(w, p.y));
+    r.x = fsub(csqr(m), fdbl(s));
+    r.y = fsub(cmul(m, fsub(s, r.x)), cmul(w, p.y));
     r.zz = v;
     r.zzz = w;
     return r;
@@ -62,15 +62,15 @@ HD_COLD Xyzz<F> ec_dbl(const Xyzz<F> &p) {
     if (p.is_zero()) return p;
     Xyzz<F> r;
     F u = fdbl(p.y);
-    F v = fsqr(u);
-    F w = fmul(u, v);
-    F s = fmul(p.x, v);
-    F xx = fsqr(p.x);
+    F v = csqr(u);
+    F w = cmul(u, v);
+    F s = cmul(p.x, v);
+    F xx = csqr(p.x);
     F m = fadd(fdbl(xx), xx);
-    r.x = fsub(fsqr(m), fdbl(s));
-    r.y = fsub(fmul(m, fsub(s, r.x)), fmul(w, p.y));
-    r.zz = fmul(v, p.zz);
-    r.zzz = fmul(w, p.zzz);
+    r.x = fsub(csqr(m), fdbl(s));
+    r.y = fsub(cmul(m, fsub(s, r.x)), cmul(w, p.y));
+    r.zz = cmul(v, p.zz);
+    r.zzz = cmul(w, p.zzz);
     return r;
 }
 
@@ -133,10 +133,10 @@ template <class F>
 HD_COLD void ec_add(Xyzz<F> &acc, const Xyzz<F> &q) {
     if (q.is_zero()) return;
     if (acc.is_zero()) { acc = q; return; }
-    F u1 = fmul(acc.x, q.zz);
-    F u2 = fmul(q.x, acc.zz);
-    F s1 = fmul(acc.y, q.zzz);
-    F s2 = fmul(q.y, acc.zzz);
+    F u1 = cmul(acc.x, q.zz);
+    F u2 = cmul(q.x, acc.zz);
+    F s1 = cmul(acc.y, q.zzz);
+    F s2 = cmul(q.y, acc.zzz);
     F p = fsub(u2, u1);
     F r = fsub(s2, s1);
     if (p.is_zero()) {
@@ -144,15 +144,15 @@ HD_COLD void ec_add(Xyzz<F> &acc, const Xyzz<F> &q) {
         else acc = Xyzz<F>::zero();
         return;
     }
-    F pp = fsqr(p);
-    F ppp = fmul(p, pp);
-    F qq = fmul(u1, pp);
-    F x3 = fsub(fsub(fsqr(r), ppp), fdbl(qq));
-    F y3 = fsub(fmul(r, fsub(qq, x3)), fmul(s1, ppp));
+    F pp = csqr(p);
+    F ppp = cmul(p, pp);
+    F qq = cmul(u1, pp);
+    F x3 = fsub(fsub(csqr(r), ppp), fdbl(qq));
+    F y3 = fsub(cmul(r, fsub(qq, x3)), cmul(s1, ppp));
     acc.x = x3;
     acc.y = y3;
-    acc.zz = fmul(fmul(acc.zz, q.zz), pp);
-    acc.zzz = fmul(fmul(acc.zzz, q.zzz), ppp);
+    acc.zz = cmul(cmul(acc.zz, q.zz), pp);
+    acc.zzz = cmul(cmul(acc.zzz, q.zzz), ppp);
 }
 
 template <class F>

@@ -70,4 +70,12 @@ HD Fq2T<B> finv(const Fq2T<B> &x) {
     return r;
 }
 
+// Products as called from the COLD group operations (full add, doubling: bucket folding / reduction, table
+// building).  For Fq2 they are out-of-line on the device: a fully inlined G2 addition is ~60 KB of SASS per call
+// site, and the cold kernels are latency-bound anyway; the hot mixed addition keeps using the inlined fmul/fsqr.
+template <class F> HD F cmul(const F &x, const F &y) { return fmul(x, y); }
+template <class F> HD F csqr(const F &x) { return fsqr(x); }
+template <class B> HD_COLD Fq2T<B> cmul(const Fq2T<B> &x, const Fq2T<B> &y) { return fmul(x, y); }
+template <class B> HD_COLD Fq2T<B> csqr(const Fq2T<B> &x) { return fsqr(x); }
+
 }  // namespace b200

@@ -66,7 +66,8 @@ inline int msm_auto_c(uint64_t n) {
     return c;
 }
 
-inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool shared_buckets) {
+inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool shared_buckets, int target_log2 = 0) {
+    const uint64_t target_tasks = target_log2 > 0 ? (1ull << target_log2) : MSM_TARGET_TASKS;
     MsmGeom g;
     int nbits = (int)scalar_size * 8;
     g.c = c;
@@ -80,9 +81,11 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     uint64_t avg = ent / g.NB + 1;
     u32 cap = 32;
     if ((ent < g.NB ? ent : g.NB) >= (1u << 18)) { while (cap < 4 * avg && cap < MSM_MAX_CAP) cap <<= 1; }
-    else { while ((uint64_t)cap * 2 * MSM_TARGET_TASKS <= ent && cap < MSM_MAX_CAP) cap <<= 1; }
+    else { while ((uint64_t)cap * 2 * target_tasks <= ent && cap < MSM_MAX_CAP) cap <<= 1; }
     g.CAP = cap;
-    g.L = g.nbk >= 16 ? 16 : g.nbk;
+    // reduce segments: longer for big bucket sets (amortises the per-segment multiplier, keeps the side-stream
+    // kernel's footprint to a few dozen CTAs)
+    g.L = g.nbk >= (1u << 18) ? 64 : g.nbk >= (1u << 17) ? 32 : g.nbk >= 16 ? 16 : g.nbk;
     g.nseg = g.nbk / g.L;
     return g;
 }
@@ -431,19 +434,22 @@ __global__ void __launch_bounds__(128) k_msm_reduce_segments(const Xyzz<F> *__re
     st_struct(seg_out + g, acc);
 }
 
+// plain sums: CTA (chunk, set) adds its slice of the set's nitems points; out[set * nchunk + chunk]
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_window_sum(const Xyzz<F> *__restrict__ seg_in, u32 nseg,
-                                                          Xyzz<F> *__restrict__ win_out) {
+__global__ void __launch_bounds__(128) k_msm_window_sum(const Xyzz<F> *__restrict__ in, u32 nitems, u32 nchunk,
+                                                          Xyzz<F> *__restrict__ out) {
     extern __shared__ uint4 smem_raw[];
     Xyzz<F> *sm = reinterpret_cast<Xyzz<F> *>(smem_raw);
-    u32 w = blockIdx.x;
+    const u32 chunk = blockIdx.x, w = blockIdx.y;
+    const u32 per = (nitems + nchunk - 1) / nchunk;
+    const u32 lo = chunk * per, hi = (lo + per < nitems) ? lo + per : nitems;
     Xyzz<F> acc = Xyzz<F>::zero();
-    for (u32 s = threadIdx.x; s < nseg; s += blockDim.x) {
-        Xyzz<F> q = ld_struct(seg_in + (size_t)w * nseg + s);
+    for (u32 s = lo + threadIdx.x; s < hi; s += blockDim.x) {
+        Xyzz<F> q = ld_struct(in + (size_t)w * nitems + s);
         ec_add(acc, q);
     }
     cta_tree_sum(acc, sm);
-    if (threadIdx.x == 0) st_struct(win_out + w, acc);
+    if (threadIdx.x == 0) st_struct(out + (size_t)w * nchunk + chunk, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -520,7 +526,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const u32 batch_max = n < MSM_MAX_BATCH ? (u32)n : MSM_MAX_BATCH;
     int c = pre ? table->c : msm_auto_c(n);
     if (!pre && ctx->force_c >= 4 && ctx->force_c <= 20) c = ctx->force_c;
-    MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre);
+    MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre, ctx->opt_target_tasks_log2);
     if (g.nwin > MSM_MAX_WIN) { ctx->err = "msm: too many windows"; return B200_ERR_ARG; }
     if (pre && (uint64_t)g.nwin * n >= (1ull << 31)) { ctx->err = "msm: table too large for 31-bit entries"; return B200_ERR_ARG; }
     if (reuse_sort && (n > batch_max)) { ctx->err = "msm: reuse_sort needs a single batch"; return B200_ERR_ARG; }
@@ -532,18 +538,17 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const u32 total_segs = g.nwin_b * g.nseg;
     const size_t PT_MAX = sizeof(G2Xyzz);   // G1 and G2 calls share the buffers: size for the larger point
 
-    const int bb = ctx->next_bucket_buf;
-    ctx->next_bucket_buf ^= 1;
+    const int bb = slot;   // every result slot owns its bucket / partial / segment buffers
     B200_TRY(ctx_reserve(ctx, ctx->w_hist, hist_len * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_cursor, hist_len * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_scan_totals, (size_t)ntiles * 4 + 16));
     B200_TRY(ctx_reserve(ctx, ctx->w_entries, max_entries * 4 + 16));
     B200_TRY(ctx_reserve(ctx, ctx->w_buckets[bb], (size_t)g.NB * PT_MAX));
-    B200_TRY(ctx_reserve(ctx, ctx->w_partial, max_partials * PT_MAX));
+    B200_TRY(ctx_reserve(ctx, ctx->w_partial[bb], max_partials * PT_MAX));
     B200_TRY(ctx_reserve(ctx, ctx->w_hot, ((size_t)3 * g.NB + 8) * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_plan, (size_t)(2 * SCAN_TILE + 16) * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_tasks, max_tasks * sizeof(uint2)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_segs[bb], (size_t)total_segs * PT_MAX));
+    B200_TRY(ctx_reserve(ctx, ctx->w_segs[bb], ((size_t)total_segs + 128 * g.nwin_b) * PT_MAX));
     B200_TRY(ctx_reserve(ctx, ctx->w_win, (size_t)Ctx::MSM_SLOTS * MSM_MAX_WIN * PT_MAX));
     B200_TRY(ctx_pinned(ctx, (size_t)Ctx::MSM_SLOTS * MSM_MAX_WIN * PT_MAX));
 
@@ -553,18 +558,17 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     // plan buffer: [0..4095] task-length histogram (then its scan), [4096..8191] scan cursors, [8192..] counters
     u32 *d_lenhist = (u32 *)ctx->w_plan.p, *d_lencur = d_lenhist + SCAN_TILE, *d_plan = d_lenhist + 2 * SCAN_TILE;
     uint2 *d_tasks = (uint2 *)ctx->w_tasks.p;
-    Pt *d_buckets = (Pt *)ctx->w_buckets[bb].p, *d_partial = (Pt *)ctx->w_partial.p;
+    Pt *d_buckets = (Pt *)ctx->w_buckets[bb].p, *d_partial = (Pt *)ctx->w_partial[bb].p;
     Pt *d_segs = (Pt *)ctx->w_segs[bb].p;
     Pt *d_win = (Pt *)((uint8_t *)ctx->w_win.p + (size_t)slot * MSM_MAX_WIN * PT_MAX);
     Pt *h_win = (Pt *)((uint8_t *)ctx->pinned + (size_t)slot * MSM_MAX_WIN * PT_MAX);
-    cudaStream_t st = ctx->stream, side = ctx->side;
+    cudaStream_t st = ctx->stream, side = ctx->side[slot];
     const bool g2 = sizeof(F) != 32;
     const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
     const size_t acc_smem_bytes = 128 * sizeof(Pt);
 
-    // this bucket buffer may still be read by the side-stream reduction of an earlier MSM
-    if (ctx->bucket_buf_slot[bb] >= 0) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_done[ctx->bucket_buf_slot[bb]], 0));
-    ctx->bucket_buf_slot[bb] = slot;
+    // this slot's buffers may still be read by the side-stream reduction of its previous MSM
+    if (ctx->slot_busy[slot]) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_done[slot], 0));
     B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_buckets, 0, (size_t)g.NB * sizeof(Pt), st));
 
     int batch_idx = 0;
@@ -577,6 +581,10 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
         const int add_existing = batch_idx > 0 ? 1 : 0;
 
         if (!reuse_sort) {
+            // the previous MSM's side-stream merge still reads the offsets / plan of the previous sort
+            for (int r = 0; r < Ctx::MSM_SLOTS; r++)
+                if (ctx->sort_readers & (1u << r)) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_merge[r], 0));
+            ctx->sort_readers = 0;
             phase_begin(ctx, PH_MSM_SORT);
             B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_hist, 0, hist_len * 4, st));
             B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_lenhist, 0, (size_t)(2 * SCAN_TILE + 16) * 4, st));
@@ -607,21 +615,39 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
         }
         phase_end(ctx);
 
-        phase_begin(ctx, PH_MSM_MERGE);
-        B200_LAUNCH(ctx, k_msm_merge_warm<F>, 4 * ctx->sm_count, 128, 0, d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_warm_list);
-        B200_LAUNCH(ctx, k_msm_merge_hot<F>, 2 * ctx->sm_count, 128, 128 * sizeof(Pt), d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_hot_list);
-        phase_end(ctx);
+        // folding of split buckets: on the side stream for the last (usually only) batch so that it overlaps the
+        // next MSM's sort and accumulation; earlier batches must finish before the next batch accumulates
+        const bool last_batch = base + batch_max >= n;
+        cudaStream_t ms = last_batch ? side : st;
+        if (last_batch) {
+            B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_acc[slot], st));
+            B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(side, ctx->ev_acc[slot], 0));
+        }
+        phase_begin(ctx, PH_MSM_MERGE, ms);
+        B200_LAUNCH_ON(ctx, ms, k_msm_merge_warm<F>, 4 * ctx->sm_count, 128, 0, d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_warm_list);
+        B200_LAUNCH_ON(ctx, ms, k_msm_merge_hot<F>, 2 * ctx->sm_count, 128, 128 * sizeof(Pt), d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_hot_list);
+        phase_end(ctx, ms);
+        if (last_batch) {
+            B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_merge[slot], side));
+            ctx->sort_readers |= 1u << slot;
+        }
     }
 
     // bucket reduction + window sums + D2H on the side stream: overlaps the next MSM's sort / accumulation
-    B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_acc[slot], st));
-    B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(side, ctx->ev_acc[slot], 0));
     phase_begin(ctx, PH_MSM_REDUCE, side);
     B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 127) / 128, 128, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
-    B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, g.nwin_b, 128, 128 * sizeof(Pt), d_segs, g.nseg, d_win);
+    {
+        // window sums in two passes: nchunk CTAs per bucket set, then one CTA per set over the chunk sums
+        u32 nchunk = (g.nseg + 1023) / 1024;
+        if (nchunk > 128) nchunk = 128;
+        Pt *d_chunk = d_segs + total_segs;
+        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(nchunk, g.nwin_b), 128, 128 * sizeof(Pt), d_segs, g.nseg, nchunk, d_chunk);
+        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, g.nwin_b), 128, 128 * sizeof(Pt), d_chunk, nchunk, 1u, d_win);
+    }
     phase_end(ctx, side);
     B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * sizeof(Pt), cudaMemcpyDeviceToHost, side));
     B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_done[slot], side));
+    ctx->slot_busy[slot] = true;
     si.nwin_b = (int)g.nwin_b; si.nwin = g.nwin; si.c = g.c; si.used = true;
     return B200_OK;
 }
@@ -634,6 +660,7 @@ int msm_collect_impl(Ctx *ctx, int slot, Xyzz<F> *out_host) {
     si.used = false;
     if (si.nwin_b == 0) { *out_host = Pt::zero(); return B200_OK; }
     B200_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev_done[slot]));
+    ctx->slot_busy[slot] = false;
     const Pt *h_win = (const Pt *)((const uint8_t *)ctx->pinned + (size_t)slot * MSM_MAX_WIN * sizeof(G2Xyzz));
     // Horner over the windows (multiexp.cpp:137-141) on the host's 4x64 field
     if (si.nwin_b == 1) *out_host = h_win[0];

@@ -249,13 +249,19 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     ZK_TRY(upload_slice(c, &zk->d_H, d->points_h, zk->rH));
     // resident per-window tables (msm.cuh): all windows of an MSM share one bucket set
     {
-        int pc = c->opt_precomp_c > 0 ? c->opt_precomp_c : 16;
-        int rows = msm_table_windows(pc);
+        // window width of the tables: about log2(points) (measured on B200: 2^20 points -> c = 20 beats 16..19),
+        // no tables at all for tiny shards where the plain multi-window path is just as fast
+        uint64_t len_max = std::max<uint64_t>(zk->rA.hi - zk->rA.lo, zk->rH.hi - zk->rH.lo);
+        int lg = 0;
+        while ((2ull << lg) <= len_max) lg++;
+        int pc = c->opt_precomp_c > 0 ? c->opt_precomp_c : std::min(20, std::max(11, lg));
+        if (c->opt_precomp_c <= 0 && lg < 11) pc = 0;
+        int rows = pc > 0 ? msm_table_windows(pc) : 0;
         uint64_t lenA = zk->rA.hi - zk->rA.lo, lenC = lenA, lenH = zk->rH.hi - zk->rH.lo;
         uint64_t need = (uint64_t)rows * ((2 * lenA + lenC + lenH) * 64 + lenA * 128);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        bool want = c->opt_precomp != 0 && pc >= 11 && pc <= 22 && need < (uint64_t)(free_b * 0.6) &&
+        bool want = c->opt_precomp != 0 && pc >= 11 && pc <= 22 && rows <= 24 && need < (uint64_t)(free_b * 0.6) &&
                     (uint64_t)rows * lenH < (1ull << 31) && (uint64_t)rows * lenA < (1ull << 31);
         if (want) {
             auto build1 = [&](G1Affine **slice, uint64_t len, MsmTableRaw *t) -> int {
@@ -297,18 +303,34 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     return B200_OK;
 }
 
-static int h_on_device(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device) {
+// witness upload, then a,b,c -> h.  With `overlap` the H pipeline runs on its own stream (c->hstream) so that
+// the witness MSMs, which do not depend on it, can start right after the upload; the caller makes the H MSM
+// wait on c->ev_h.
+static int h_on_device(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, bool overlap = false) {
     phase_begin(c, PH_H2D);
     B200_CUDA_CHECK(c, cudaMemcpyAsync(zk->d_wtns, wtns, (size_t)zk->n_vars * 32,
                                         wtns_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     phase_end(c);
+    cudaStream_t main_stream = c->stream;
+    if (overlap) {
+        B200_CUDA_CHECK(c, cudaEventRecord(c->ev_h, main_stream));
+        B200_CUDA_CHECK(c, cudaStreamWaitEvent(c->hstream, c->ev_h, 0));
+        c->stream = c->hstream;           // build_abc / h_pipeline launch on c->stream
+    }
+    int rc = B200_OK;
     phase_begin(c, PH_BUILD_AB);
-    B200_TRY(build_abc(c, zk->d_wtns, zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->domain_size, zk->d_a, zk->d_b, zk->d_c));
+    rc = build_abc(c, zk->d_wtns, zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->domain_size, zk->d_a, zk->d_b, zk->d_c);
     phase_end(c);
-    phase_begin(c, PH_NTT);
-    B200_TRY(h_pipeline(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size));
-    phase_end(c);
-    return B200_OK;
+    if (rc == B200_OK) {
+        phase_begin(c, PH_NTT);
+        rc = h_pipeline(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size);
+        phase_end(c);
+    }
+    if (overlap) {
+        if (rc == B200_OK && cudaEventRecord(c->ev_h, c->hstream) != cudaSuccess) rc = B200_ERR_CUDA;
+        c->stream = main_stream;
+    }
+    return rc;
 }
 
 int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_out_host) {
@@ -328,7 +350,7 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     phase_reset(c);
-    B200_TRY(h_on_device(c, zk, wtns_host, wtns_on_device));
+    B200_TRY(h_on_device(c, zk, wtns_host, wtns_on_device, true));
     uint8_t *o = (uint8_t *)out768;
     G1Xyzz pih, pia, pib1, pic;
     G2Xyzz pib;
@@ -339,18 +361,21 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     const uint64_t lenA = zk->rA.hi - zk->rA.lo;
     const bool same_geom = (!zk->tA.tbl == !zk->tB1.tbl) && (!zk->tA.tbl == !zk->tB2.tbl) && (!zk->tA.tbl == !zk->tC.tbl) &&
                            lenA <= (1u << 24);
-    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH));
+    // order: the G2 MSM first (its long bucket reduction then hides behind four G1 accumulations), H last
     B200_TRY(msm_g2_enqueue(c, zk->d_B2, w + zk->rA.lo * 32, 32, lenA, 1, &zk->tB2));
     B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom));
     B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom));
     B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom));
+    B200_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_h, 0));   // h scalars ready (H pipeline stream)
+    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH));
     B200_TRY(msm_g1_collect(c, 0, &pih));
     B200_TRY(msm_g2_collect(c, 1, &pib));
     B200_TRY(msm_g1_collect(c, 2, &pia));
     B200_TRY(msm_g1_collect(c, 3, &pib1));
     B200_TRY(msm_g1_collect(c, 4, &pic));
     B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->side));
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) B200_CUDA_CHECK(c, cudaStreamSynchronize(c->side[i]));
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->hstream));
     phase_collect(c);
     memcpy(o, &pih, 128);
     memcpy(o + 128, &pia, 128);

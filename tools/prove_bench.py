@@ -30,7 +30,7 @@ def main():
     coefs = s.coefs_section()
     for cfg in args.configs:
         opts = dict(kv.split("=") for kv in cfg.split(",") if kv)
-        for k in ("precomp", "precomp_c", "acc_smem", "msm_window"):
+        for k in ("precomp", "precomp_c", "acc_smem", "msm_window", "target_tasks_log2"):
             ctx.set_option(k, int(opts.get(k, -1 if k in ("precomp", "acc_smem") else 0)))
         t0 = time.time()
         zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"])
