@@ -33,11 +33,12 @@ int b200_init(int device, b200_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->c.hstream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_h, cudaEventDisableTiming);
-    if (e == cudaSuccess) {   // side stream (bucket folding / reduction): highest priority so its few CTAs are not starved
+    if (e == cudaSuccess) {   // side streams (H pipeline; bucket folding / reduction): highest priority so their CTAs are
+                              // placed as soon as an accumulation CTA retires instead of waiting for its grid to drain
         int lo_p = 0, hi_p = 0;
         cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        e = cudaStreamCreateWithPriority(&h->c.hstream, cudaStreamNonBlocking, hi_p);
         for (int i = 0; i < Ctx::MSM_SLOTS && e == cudaSuccess; i++)
             e = cudaStreamCreateWithPriority(&h->c.side[i], cudaStreamNonBlocking, hi_p);
     }

@@ -1,0 +1,177 @@
+"""Golden vectors produced by the reference itself (tests/golden/make_golden.py -> golden_v1.json):
+CPU checks of the oracle port and of the product's host side here; the GPU checks live at the bottom
+(marked gpu) and include the CLI producing byte-identical proof.json / public.json."""
+import ctypes
+import json
+import os
+import subprocess
+
+import pytest
+
+import bn254 as bn
+import oracle_lib
+import rapidsnark_old_b200 as b200
+
+ROOT = oracle_lib.ROOT
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_v1.json")))
+C = G["circuit_2_4"]
+PROVER = os.path.join(ROOT, "build", "prover")
+
+
+def _sections(raw):
+    """iden3 binfile -> {type: payload}"""
+    n = int.from_bytes(raw[8:12], "little")
+    pos, out = 12, {}
+    for _ in range(n):
+        typ = int.from_bytes(raw[pos:pos + 4], "little")
+        size = int.from_bytes(raw[pos + 4:pos + 12], "little")
+        out.setdefault(typ, raw[pos + 12:pos + 12 + size])
+        pos += 12 + size
+    return out
+
+
+def _circuit():
+    z = _sections(bytes.fromhex(C["zkey"]))
+    w = _sections(bytes.fromhex(C["wtns"]))
+    hdr = z[2]
+    n_vars, n_public, domain = (int.from_bytes(hdr[72 + 4 * i:76 + 4 * i], "little") for i in range(3))
+    vk = {"alpha1": hdr[84:148], "beta1": hdr[148:212], "beta2": hdr[212:340], "gamma2": hdr[340:468],
+          "delta1": hdr[468:532], "delta2": hdr[532:660]}
+    return dict(n_vars=n_vars, n_public=n_public, domain=domain, n_coefs=len(z[4]) // 44, coefs=z[4], A=z[5], B1=z[6],
+                B2=z[7], C=z[8], H=z[9], vk=vk, wtns=w[2])
+
+
+def _affine_to_xyzz(aff, g2=False):
+    one = bn.to_mont(1)
+    if g2:
+        return aff if aff == bytes(128) and False else aff + (one + bytes(32)) * 2
+    return aff + one * 2
+
+
+# ----------------------------------------------------------------------------- CPU
+def test_port_oracle_matches_reference_golden():
+    o = oracle_lib.port()
+    m = G["msm_g1"]
+    assert o.g1_to_affine(o.g1_msm(bytes.fromhex(m["bases"]), bytes.fromhex(m["scalars"]), m["n"])).hex() == m["affine"]
+    m = G["msm_g2"]
+    assert o.g2_to_affine(o.g2_msm(bytes.fromhex(m["bases"]), bytes.fromhex(m["scalars"]), m["n"])).hex() == m["affine"]
+    t = G["ntt"]
+    assert o.fr_fft(bytes.fromhex(t["in"])).hex() == t["fft"]
+    assert o.fr_ifft(bytes.fromhex(t["in"])).hex() == t["ifft"]
+    c = _circuit()
+    assert o.h_scalars(c["domain"], c["n_coefs"], c["coefs"], c["wtns"]).hex() == C["h_scalars"]
+    msms = o.prove_msms(c["n_vars"], c["n_public"], c["domain"], c["n_coefs"], c["coefs"], c["A"], c["B1"], c["B2"],
+                        c["C"], c["H"], c["wtns"])
+    assert [a.hex() for a in o.msms_to_affine(msms)] == C["msms_affine"]
+    vk = c["vk"]
+    proof = o.blind(msms, vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"], vk["delta2"], bytes.fromhex(C["r"]),
+                    bytes.fromhex(C["s"]))
+    assert proof.hex() == C["proof"]
+
+
+def test_host_finalize_and_json_match_reference_cli_golden():
+    c = _circuit()
+    a = [bytes.fromhex(x) for x in C["msms_affine"]]
+    msms = (_affine_to_xyzz(a[0]) + _affine_to_xyzz(a[1]) + _affine_to_xyzz(a[2]) + _affine_to_xyzz(a[3], True) +
+            _affine_to_xyzz(a[4]))
+    proof = b200.groth16_finalize(msms, c["vk"], bytes.fromhex(C["r"]), bytes.fromhex(C["s"]))
+    assert proof.hex() == C["proof"]
+    assert b200.proof_json(proof) == C["proof_json"]       # byte-identical to the reference CLI's proof.json
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from rapidsnark_old_b200 import dist as bdist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    o = oracle_lib.port()
+    c = _circuit()
+    # this rank's point-range shard, computed by the oracle (no GPU here): same partition as b200_zkey_upload
+    lo, hi = bdist.shard_range(c["n_vars"], rank, world)
+    hlo, hhi = bdist.shard_range(c["domain"], rank, world)
+    h = o.h_scalars(c["domain"], c["n_coefs"], c["coefs"], c["wtns"])
+    w = c["wtns"]
+    skip = c["n_public"] + 1
+    clo, chi = max(lo, skip), max(hi, skip)
+    part = (o.g1_msm(c["H"][64 * hlo:64 * hhi], h[32 * hlo:32 * hhi], hhi - hlo) +
+            o.g1_msm(c["A"][64 * lo:64 * hi], w[32 * lo:32 * hi], hi - lo) +
+            o.g1_msm(c["B1"][64 * lo:64 * hi], w[32 * lo:32 * hi], hi - lo) +
+            o.g2_msm(c["B2"][128 * lo:128 * hi], w[32 * lo:32 * hi], hi - lo) +
+            o.g1_msm(c["C"][64 * (clo - skip):64 * (chi - skip)], w[32 * clo:32 * chi], chi - clo))
+    folded, proof = bdist.finish_proof(part, c["vk"], bytes.fromhex(C["r"]), bytes.fromhex(C["s"]))
+    q.put((rank, proof.hex()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_proof_over_gloo_matches_golden(world):
+    """N > 1 host path on CPU: per-rank partial MSMs -> all_gather (gloo) -> fold -> finalize == unsharded proof."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(pr == C["proof"] for _, pr in res)
+
+
+# ----------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def gctx():
+    c = b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+def test_gpu_primitives_match_golden(gctx):
+    m = G["msm_g1"]
+    got = gctx.msm_g1(bytes.fromhex(m["bases"]), bytes.fromhex(m["scalars"]), m["n"])
+    assert b200.host_g1_to_affine(got).hex() == m["affine"]
+    m = G["msm_g2"]
+    got = gctx.msm_g2(bytes.fromhex(m["bases"]), bytes.fromhex(m["scalars"]), m["n"])
+    assert b200.host_g2_to_affine(got).hex() == m["affine"]
+    t = G["ntt"]
+    assert gctx.ntt(bytes.fromhex(t["in"])).hex() == t["fft"]
+    assert gctx.ntt(bytes.fromhex(t["in"]), inverse=True).hex() == t["ifft"]
+
+
+@pytest.mark.gpu
+def test_gpu_prove_matches_golden(gctx):
+    c = _circuit()
+    zk = gctx.zkey_upload(c["n_vars"], c["n_public"], c["domain"], c["n_coefs"], c["coefs"], c["A"], c["B1"], c["B2"],
+                          c["C"], c["H"])
+    assert zk.h_scalars(c["wtns"]).hex() == C["h_scalars"]
+    msms = zk.prove_msms(c["wtns"])
+    aff = [b200.host_g1_to_affine(msms[0:128]), b200.host_g1_to_affine(msms[128:256]),
+           b200.host_g1_to_affine(msms[256:384]), b200.host_g2_to_affine(msms[384:640]),
+           b200.host_g1_to_affine(msms[640:768])]
+    assert [a.hex() for a in aff] == C["msms_affine"]
+    proof = b200.groth16_finalize(msms, c["vk"], bytes.fromhex(C["r"]), bytes.fromhex(C["s"]))
+    assert proof.hex() == C["proof"]
+    zk.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", ["1", "2"])
+def test_cli_output_is_byte_identical_to_reference_cli(tmp_path, gpus):
+    """build/prover <zkey> <wtns> <proof.json> <public.json> vs the reference CLI's files for the same r, s.
+    B200_GPUS=2 runs two point-range shards (on one physical GPU if only one is present: B200_DEVICE stride 0)."""
+    zk, wt = tmp_path / "c.zkey", tmp_path / "w.wtns"
+    zk.write_bytes(bytes.fromhex(C["zkey"]))
+    wt.write_bytes(bytes.fromhex(C["wtns"]))
+    env = dict(os.environ, B200_R=bytes.fromhex(C["r"])[::-1].hex(), B200_S=bytes.fromhex(C["s"])[::-1].hex())
+    if gpus != "1":
+        import torch
+        if torch.cuda.device_count() < int(gpus):
+            pytest.skip("needs %s GPUs" % gpus)
+        env["B200_GPUS"] = gpus
+    r = subprocess.run([PROVER, str(zk), str(wt), str(tmp_path / "proof.json"), str(tmp_path / "public.json")],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "proof.json").read_text() == C["proof_json"]
+    assert (tmp_path / "public.json").read_text() == C["public_json"]
