@@ -185,10 +185,11 @@ int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t sc
 int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G2Xyzz *out_host,
                const MsmTableRaw *table = nullptr);
 // asynchronous pair: enqueue all kernels of one MSM (result lands in pinned slot `slot`), collect = wait + host Horner
+// `tail`: no further MSM follows (nothing to overlap the bucket reduction with)
 int msm_g1_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
-                   const MsmTableRaw *table = nullptr, bool reuse_sort = false);
+                   const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true);
 int msm_g2_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
-                   const MsmTableRaw *table = nullptr, bool reuse_sort = false);
+                   const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true);
 int msm_g1_collect(Ctx *ctx, int slot, G1Xyzz *out_host);
 int msm_g2_collect(Ctx *ctx, int slot, G2Xyzz *out_host);
 int msm_g1_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl);

@@ -66,7 +66,8 @@ inline int msm_auto_c(uint64_t n) {
     return c;
 }
 
-inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool shared_buckets, int target_log2 = 0) {
+inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool shared_buckets, int target_log2 = 0,
+                            bool tail = false) {
     const uint64_t target_tasks = target_log2 > 0 ? (1ull << target_log2) : MSM_TARGET_TASKS;
     MsmGeom g;
     int nbits = (int)scalar_size * 8;
@@ -86,6 +87,7 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     // reduce segments: longer for big bucket sets (amortises the per-segment multiplier, keeps the side-stream
     // kernel's footprint to a few dozen CTAs)
     g.L = g.nbk >= (1u << 18) ? 64 : g.nbk >= (1u << 17) ? 32 : g.nbk >= 16 ? 16 : g.nbk;
+    if (tail && g.L > 16) g.L = 16;   // nothing left to overlap with: shortest chains, the whole GPU is free
     g.nseg = g.nbk / g.L;
     return g;
 }
@@ -411,8 +413,11 @@ __global__ void __launch_bounds__(128) k_msm_merge_hot(const u32 *__restrict__ o
 // ------------------------------------------------------------------------------------------------
 // 6: sum_k (k+1) * B[w][k]  (reference: reduce, multiexp.cpp:62-96 - different recursion, same value)
 // ------------------------------------------------------------------------------------------------
+// Launched with 32-thread CTAs and <= 168 registers: ~5 K registers per CTA slip in next to the three resident
+// accumulation CTAs of an SM (3 x 18 K of 64 K) instead of evicting two of them, which is what a 128-thread /
+// 255-register CTA did (ncu launch list, profiles/r01_*: the reductions were 28% of the serialised time).
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_reduce_segments(const Xyzz<F> *__restrict__ buckets, u32 nbk, u32 L,
+__global__ void __launch_bounds__(128, 3) k_msm_reduce_segments(const Xyzz<F> *__restrict__ buckets, u32 nbk, u32 L,
                                                                u32 nseg, u32 total_segs,
                                                                Xyzz<F> *__restrict__ seg_out) {
     u32 g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -510,7 +515,7 @@ int msm_precompute_table(Ctx *ctx, const Affine<F> *d_pts, u32 n, int c, Affine<
 
 template <class F>
 int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint32_t scalar_size, uint64_t n, int slot,
-                     const MsmTable<F> *table, bool reuse_sort) {
+                     const MsmTable<F> *table, bool reuse_sort, bool tail) {
     typedef Xyzz<F> Pt;
     if (slot < 0 || slot >= Ctx::MSM_SLOTS) { ctx->err = "msm: bad result slot"; return B200_ERR_ARG; }
     Ctx::SlotInfo &si = ctx->slot_info[slot];
@@ -526,7 +531,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const u32 batch_max = n < MSM_MAX_BATCH ? (u32)n : MSM_MAX_BATCH;
     int c = pre ? table->c : msm_auto_c(n);
     if (!pre && ctx->force_c >= 4 && ctx->force_c <= 20) c = ctx->force_c;
-    MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre, ctx->opt_target_tasks_log2);
+    MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre, ctx->opt_target_tasks_log2, tail);
     if (g.nwin > MSM_MAX_WIN) { ctx->err = "msm: too many windows"; return B200_ERR_ARG; }
     if (pre && (uint64_t)g.nwin * n >= (1ull << 31)) { ctx->err = "msm: table too large for 31-bit entries"; return B200_ERR_ARG; }
     if (reuse_sort && (n > batch_max)) { ctx->err = "msm: reuse_sort needs a single batch"; return B200_ERR_ARG; }
@@ -635,7 +640,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
 
     // bucket reduction + window sums + D2H on the side stream: overlaps the next MSM's sort / accumulation
     phase_begin(ctx, PH_MSM_REDUCE, side);
-    B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 127) / 128, 128, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
+    B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 31) / 32, 32, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
     {
         // window sums in two passes: nchunk CTAs per bucket set, then one CTA per set over the chunk sums
         u32 nchunk = (g.nseg + 1023) / 1024;

@@ -362,12 +362,12 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     const bool same_geom = (!zk->tA.tbl == !zk->tB1.tbl) && (!zk->tA.tbl == !zk->tB2.tbl) && (!zk->tA.tbl == !zk->tC.tbl) &&
                            lenA <= (1u << 24);
     // order: the G2 MSM first (its long bucket reduction then hides behind four G1 accumulations), H last
-    B200_TRY(msm_g2_enqueue(c, zk->d_B2, w + zk->rA.lo * 32, 32, lenA, 1, &zk->tB2));
-    B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom));
-    B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom));
-    B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom));
+    B200_TRY(msm_g2_enqueue(c, zk->d_B2, w + zk->rA.lo * 32, 32, lenA, 1, &zk->tB2, false, false));
+    B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom, false));
+    B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom, false));
+    B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom, false));
     B200_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_h, 0));   // h scalars ready (H pipeline stream)
-    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH));
+    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true));
     B200_TRY(msm_g1_collect(c, 0, &pih));
     B200_TRY(msm_g2_collect(c, 1, &pib));
     B200_TRY(msm_g1_collect(c, 2, &pia));
