@@ -199,15 +199,12 @@ def run_own(args):
     wt_dev = wt_host.cuda()
     r32, s32 = (12345).to_bytes(32, "little"), (67890).to_bytes(32, "little")
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    gather_dev = torch.empty(world * 768, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    from rapidsnark_old_b200 import dist as bdist
 
     def finish(part):
-        if world > 1:
-            mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).cuda()
-            dist.all_gather_into_tensor(gather_dev, mine)          # the one collective of the path (NCCL)
-            allp = bytes(gather_dev.cpu().numpy())
-            part = b200.fold_partials([allp[i * 768:(i + 1) * 768] for i in range(world)])
-        return part, b200.groth16_finalize(part, vk, r32, s32)
+        # N > 1: the one collective of the path - all_gather of the 768-byte partial records (NCCL), fold, finalize
+        return bdist.finish_proof(part, vk, r32, s32, device=torch.device("cuda", local))
 
     def step_resident():
         return finish(zk.prove_msms_dev(wt_dev.data_ptr()))
@@ -259,7 +256,7 @@ def run_own(args):
     acc_ms = ph_res.get("msm_accumulate_g1", 0.0) / 4
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
     roof = {"bound": "hbm", "kernel": "k_msm_accumulate<Fq>", "achieved": round(achieved, 2), "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 5), "traffic": None, "peak_kind": pk_kind,
+            "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 5), "traffic": ncu_traffic(), "peak_kind": pk_kind,
             "launch_ms": round(acc_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
             "note": "integer-ALU bound by construction (SURVEY 8d): ~10 Montgomery products of 8x8 32-bit limbs per "
                     "96 algorithmic bytes; see DESIGN.md for the IMAD roofline"}
@@ -284,6 +281,20 @@ def run_own(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of k_msm_accumulate<Fq> from the committed
+    `ncu --set full` capture (profiles/r01_accumulate_metrics.json, N = 1 run of this command)."""
+    try:
+        ks = json.load(open(os.path.join(ROOT, "profiles", "r01_accumulate_metrics.json")))
+        g1 = [k for k in ks if k["kernel"].startswith("k_msm_accumulate<Fq,")]
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = [k["dram__bytes_read.sum"] * unit[k["dram__bytes_read.sum__unit"]] +
+               k["dram__bytes_write.sum"] * unit[k["dram__bytes_write.sum__unit"]] for k in g1]
+        return round(sum(tot) / len(tot)) if tot else None
+    except Exception:
+        return None
 
 
 def zk_len(total, rank, world):
