@@ -68,8 +68,59 @@ __global__ void __launch_bounds__(256) k_ntt_build_powers(Fr base, u32 count, Fr
     st_struct(out + i, r);
 }
 
-template <bool DIT>
-__global__ void __launch_bounds__(512) k_ntt_pass(Fr *__restrict__ a, int lo, int S, int q, NttTable tb) {
+// G butterfly stages on 2^G elements held in registers (radix-2^G step): one shared-memory round trip and one
+// barrier per G stages instead of per stage.
+//   DIF: stages with half = H, H/2, .., H/2^(G-1); the thread owns rows  blk*2H + j + m*(2H >> G), m < 2^G
+//   DIT: stages with half = h0, 2*h0, .., h0*2^(G-1); the thread owns rows  blk*(h0 << G) + j + m*h0
+// Twiddle of a butterfly whose lower row is r at a stage of half-size `half`: w_R^((r mod half) * (R/2) / half).
+template <bool DIT, int G>
+DEVFN void ntt_group(uint4 *x0, uint4 *x1, const uint4 *w0, const uint4 *w1, u32 R, int q, u32 hsel, u32 tid, u32 nthreads) {
+    const u32 Q = 1u << q;
+    const u32 stride = DIT ? hsel : ((2 * hsel) >> G);      // row distance between consecutive m
+    const u32 span = stride << G;                            // rows covered by one group instance
+    const u32 units = (R >> G) << q;                         // (group instance, j, column) triples in the tile
+    for (u32 id = tid; id < units; id += nthreads) {
+        const u32 c = id & (Q - 1), t = id >> q;
+        const u32 j = t % stride, blk = t / stride;
+        const u32 r0 = blk * span + j;
+        Fr v[1 << G];
+#pragma unroll
+        for (int m = 0; m < (1 << G); m++) v[m] = lds_fr(x0, x1, ((r0 + m * stride) << q) + c);
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+            const int bit = DIT ? s : (G - 1 - s);           // partner distance in m is 2^bit
+            const u32 half = stride << bit;
+            const u32 tw_mul = (R >> 1) / half;
+#pragma unroll
+            for (int m = 0; m < (1 << G); m++) {
+                if (m & (1 << bit)) continue;
+                const int m2 = m | (1 << bit);
+                const u32 pos = j + (u32)(m & ((1 << bit) - 1)) * stride;   // (row of m) mod half
+                if (DIT) {
+                    Fr tv = v[m2];
+                    if (pos) tv = fp_mul(tv, lds_fr(w0, w1, pos * tw_mul));
+                    Fr u = v[m];
+                    v[m] = fp_add(u, tv);
+                    v[m2] = fp_sub(u, tv);
+                } else {
+                    Fr u = v[m], w = v[m2];
+                    v[m] = fp_add(u, w);
+                    Fr d = fp_sub(u, w);
+                    if (pos) d = fp_mul(d, lds_fr(w0, w1, pos * tw_mul));
+                    v[m2] = d;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < (1 << G); m++) sts_fr(x0, x1, ((r0 + m * stride) << q) + c, v[m]);
+    }
+}
+
+// One pass over HBM: tile of 2^S rows x 2^q columns in shared memory, S stages in radix-8 (then radix-4/2) steps.
+// FUSE (DIF, lo == 0 only): the ifft tail and the coset twist of groth16.cpp:107-110 are applied on the way out:
+// position p holds coefficient bitrev(p), multiplied by n^-1 * w_2n^bitrev(p).
+template <bool DIT, bool FUSE>
+__global__ void __launch_bounds__(256, 2) k_ntt_pass(Fr *__restrict__ a, int lo, int S, int q, NttTable tb, int k, Fr n_inv) {
     extern __shared__ uint4 smem_raw[];
     const u32 R = 1u << S, Q = 1u << q, tile_elems = R << q;
     uint4 *x0 = smem_raw, *x1 = x0 + tile_elems;
@@ -97,38 +148,16 @@ __global__ void __launch_bounds__(512) k_ntt_pass(Fr *__restrict__ a, int lo, in
     }
     __syncthreads();
 
-    const u32 nbf = tile_elems >> 1;   // butterflies per stage
     if (DIT) {
-        for (u32 half = 1; half < R; half <<= 1) {
-            const u32 tw_mul = (R >> 1) / half;
-            for (u32 id = threadIdx.x; id < nbf; id += blockDim.x) {
-                u32 c = id & (Q - 1), t = id >> q;
-                u32 pos = t & (half - 1), grp = t / half;
-                u32 r0 = grp * 2 * half + pos;
-                u32 i0 = (r0 << q) + c, i1 = i0 + (half << q);
-                Fr u = lds_fr(x0, x1, i0), v = lds_fr(x0, x1, i1);
-                if (pos) v = fp_mul(v, lds_fr(w0, w1, pos * tw_mul));
-                sts_fr(x0, x1, i0, fp_add(u, v));
-                sts_fr(x0, x1, i1, fp_sub(u, v));
-            }
-            __syncthreads();
-        }
+        int done = 0;
+        while (S - done >= 3) { ntt_group<true, 3>(x0, x1, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 3; __syncthreads(); }
+        if (S - done == 2) { ntt_group<true, 2>(x0, x1, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 2; __syncthreads(); }
+        if (S - done == 1) { ntt_group<true, 1>(x0, x1, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 1; __syncthreads(); }
     } else {
-        for (u32 half = R >> 1; half >= 1; half >>= 1) {
-            const u32 tw_mul = (R >> 1) / half;
-            for (u32 id = threadIdx.x; id < nbf; id += blockDim.x) {
-                u32 c = id & (Q - 1), t = id >> q;
-                u32 pos = t & (half - 1), grp = t / half;
-                u32 r0 = grp * 2 * half + pos;
-                u32 i0 = (r0 << q) + c, i1 = i0 + (half << q);
-                Fr u = lds_fr(x0, x1, i0), v = lds_fr(x0, x1, i1);
-                Fr d = fp_sub(u, v);
-                if (pos) d = fp_mul(d, lds_fr(w0, w1, pos * tw_mul));
-                sts_fr(x0, x1, i0, fp_add(u, v));
-                sts_fr(x0, x1, i1, d);
-            }
-            __syncthreads();
-        }
+        int left = S;   // stages left; the next stage has half = 2^(left-1)
+        while (left >= 3) { ntt_group<false, 3>(x0, x1, w0, w1, R, q, 1u << (left - 1), threadIdx.x, blockDim.x); left -= 3; __syncthreads(); }
+        if (left == 2) { ntt_group<false, 2>(x0, x1, w0, w1, R, q, 2u, threadIdx.x, blockDim.x); left -= 2; __syncthreads(); }
+        if (left == 1) { ntt_group<false, 1>(x0, x1, w0, w1, R, q, 1u, threadIdx.x, blockDim.x); left -= 1; __syncthreads(); }
     }
 
     for (u32 e = threadIdx.x; e < tile_elems; e += blockDim.x) {
@@ -137,6 +166,13 @@ __global__ void __launch_bounds__(512) k_ntt_pass(Fr *__restrict__ a, int lo, in
         if (!DIT && lo > 0) {
             u32 k1 = __brev(r) >> (32 - S);
             u32 ex = ((l0 + c) * k1) << tw_shift;
+            if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
+        }
+        if (FUSE) {
+            u64 p = base + r;                                   // lo == 0, q == 0
+            u32 i = (u32)(__brevll(p) >> (64 - k));
+            u32 ex = i << (tb.s - (k + 1));
+            x = fp_mul(x, n_inv);
             if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
         }
         st_struct(a + base + ((u64)r << lo) + l0 + c, x);
@@ -280,23 +316,24 @@ static int ntt_plan(int k, NttPass *p) {   // passes ordered from the high bits 
     return np;
 }
 
-template <bool DIT>
-static int ntt_launch_pass(Ctx *ctx, Fr *d_a, int k, const NttPass &ps, const NttTable &tb) {
+template <bool DIT, bool FUSE>
+static int ntt_launch_pass(Ctx *ctx, Fr *d_a, int k, const NttPass &ps, const NttTable &tb, const Fr &n_inv) {
     if (ps.S == 0) return B200_OK;
     const u32 tile_elems = 1u << (ps.S + ps.q);
     const size_t smem = (size_t)tile_elems * 32 + (size_t)(1u << (ps.S - 1)) * 32;
     const u32 grid = (u32)(((u64)1 << k) >> (ps.S + ps.q));
-    u32 threads = tile_elems / 2;
-    if (threads > 512) threads = 512;
+    u32 threads = tile_elems / 8;
+    if (threads > 256) threads = 256;
     if (threads < 32) threads = 32;
-    auto kern = k_ntt_pass<DIT>;
+    auto kern = k_ntt_pass<DIT, FUSE>;
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    B200_LAUNCH(ctx, kern, grid, threads, smem, d_a, ps.lo, ps.S, ps.q, tb);
+    B200_LAUNCH(ctx, kern, grid, threads, smem, d_a, ps.lo, ps.S, ps.q, tb, k, n_inv);
     return B200_OK;
 }
 
@@ -307,14 +344,26 @@ static int ilog2_exact(uint64_t n) {
     return k;
 }
 
-// natural -> bit-reversed (DIF)
-int ntt_dif(Ctx *ctx, Fr *d_a, int k, bool inverse_roots) {
+// natural -> bit-reversed (DIF).  fuse_scale_twist: multiply the result by n^-1 * w_2n^(natural index) on the way
+// out of the last pass (the forward table `tw` supplies the coset roots).
+int ntt_dif(Ctx *ctx, Fr *d_a, int k, bool inverse_roots, const Fr *n_inv = nullptr) {
     if (k == 0) return B200_OK;
     NttTable tb;
     B200_TRY(ntt_get_table(ctx, k, inverse_roots, &tb));
     NttPass p[8];
     int np = ntt_plan(k, p);
-    for (int i = 0; i < np; i++) B200_TRY(ntt_launch_pass<false>(ctx, d_a, k, p[i], tb));
+    Fr one = Fr::one();
+    for (int i = 0; i < np; i++) {
+        if (n_inv && i == np - 1) {
+            // the coset twist uses FORWARD roots while the passes use inverse ones: hand the forward two-level table
+            NttTable tf, mix = tb;
+            B200_TRY(ntt_get_table(ctx, k, false, &tf));
+            mix.t_lo = tf.t_lo; mix.t_hi = tf.t_hi;       // last pass has lo == 0: t_lo/t_hi are only read by the twist
+            B200_TRY((ntt_launch_pass<false, true>(ctx, d_a, k, p[i], mix, *n_inv)));
+        } else {
+            B200_TRY((ntt_launch_pass<false, false>(ctx, d_a, k, p[i], tb, one)));
+        }
+    }
     return B200_OK;
 }
 
@@ -325,7 +374,8 @@ int ntt_dit(Ctx *ctx, Fr *d_a, int k, bool inverse_roots) {
     B200_TRY(ntt_get_table(ctx, k, inverse_roots, &tb));
     NttPass p[8];
     int np = ntt_plan(k, p);
-    for (int i = np - 1; i >= 0; i--) B200_TRY(ntt_launch_pass<true>(ctx, d_a, k, p[i], tb));
+    Fr one = Fr::one();
+    for (int i = np - 1; i >= 0; i--) B200_TRY((ntt_launch_pass<true, false>(ctx, d_a, k, p[i], tb, one)));
     return B200_OK;
 }
 
@@ -360,8 +410,11 @@ int h_pipeline(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n) {
     Fr ninv = host_n_inv(k);
     Fr *arr[3] = {d_a, d_b, d_c};
     for (int i = 0; i < 3; i++) {
-        B200_TRY(ntt_dif(ctx, arr[i], k, true));
-        B200_LAUNCH(ctx, k_ntt_scale_twist_brev, (u32)((n + 255) / 256), 256, 0, arr[i], k, ninv, tf);
+        if (k == 0) {
+            B200_LAUNCH(ctx, k_ntt_scale_twist_brev, 1, 256, 0, arr[i], k, ninv, tf);
+        } else {
+            B200_TRY(ntt_dif(ctx, arr[i], k, true, &ninv));    // ifft + 1/n + coset twist, output bit-reversed
+        }
         B200_TRY(ntt_dit(ctx, arr[i], k, false));
     }
     B200_LAUNCH(ctx, k_h_combine, (u32)((n + 255) / 256), 256, 0, d_a, d_b, d_c, n);
