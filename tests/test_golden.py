@@ -175,3 +175,35 @@ def test_cli_output_is_byte_identical_to_reference_cli(tmp_path, gpus):
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "proof.json").read_text() == C["proof_json"]
     assert (tmp_path / "public.json").read_text() == C["public_json"]
+
+
+@pytest.mark.gpu
+def test_fullprover_status_machine(tmp_path):
+    """FullProver (src/fullprover.cpp:21-240): ready -> busy -> success, witness from ./build/<circuit> via popen,
+    status JSON {"proof": "<json text>", "pubData": "<json text>", "status": "success"}; the proof verifies."""
+    import stat
+    import pairing
+    from test_verifier import _proof_from_json, _vk_and_public
+    (tmp_path / "build").mkdir()
+    zk, wt = tmp_path / "mycircuit.zkey", tmp_path / "w.wtns"
+    zk.write_bytes(bytes.fromhex(C["zkey"]))
+    wt.write_bytes(bytes.fromhex(C["wtns"]))
+    gen = tmp_path / "build" / "mycircuit"          # stand-in for the circom witness calculator binary
+    gen.write_text("#!/bin/sh\ncp %s \"$2\"\necho witness done\n" % wt)
+    gen.chmod(gen.stat().st_mode | stat.S_IEXEC)
+    inp = tmp_path / "input.json"
+    inp.write_text('{"a": 1}')
+    r = subprocess.run([os.path.join(ROOT, "build", "fullprover_demo"), str(zk), "--", "mycircuit", str(inp)],
+                       capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines[0] == '{"status":"ready"}'
+    st = json.loads(lines[-1])
+    assert st["status"] == "success"
+    assert json.loads(st["pubData"]) == json.loads(C["public_json"])
+    c, vk, public = _vk_and_public()
+    assert pairing.groth16_verify(vk, _proof_from_json(st["proof"]), public)
+    # unknown circuit -> failed with an error text, like the reference's catch(std::runtime_error)
+    r = subprocess.run([os.path.join(ROOT, "build", "fullprover_demo"), str(zk), "--", "nosuch", str(inp)],
+                       capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and '"status":"failed"' in r.stdout
