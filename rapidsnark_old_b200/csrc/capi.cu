@@ -88,6 +88,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;
     else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;
     else if (!strcmp(name, "target_tasks_log2")) h->c.opt_target_tasks_log2 = value;
+    else if (!strcmp(name, "max_batch_log2")) h->c.opt_max_batch_log2 = value;
     else { h->c.err = std::string("unknown option ") + name; return B200_ERR_ARG; }
     return B200_OK;
 }

@@ -58,6 +58,7 @@ struct Ctx {
     // MSM workspaces (shared by G1/G2 calls; grow-only)
     DevBuf w_hist, w_cursor, w_entries, w_buckets[MSM_SLOTS], w_partial[MSM_SLOTS], w_hot, w_scan_totals, w_segs[MSM_SLOTS], w_win, w_plan, w_tasks;
     int opt_target_tasks_log2 = 0;     // 0 = default (msm.cuh)
+    int opt_max_batch_log2 = 0;        // 0 = default 24; smaller values exercise the multi-batch path in tests
     DevBuf w_in_bases, w_in_scalars;   // staging for host-pointer calls
     DevBuf w_ntt;                      // staging for host-pointer NTT calls
     void *pinned = nullptr;            // small pinned host buffer for results

@@ -526,9 +526,10 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const bool pre = table && table->tbl;
     const Affine<F> *d_bases = pre ? table->tbl : static_cast<const Affine<F> *>(d_bases_v);
     const uint8_t *d_scalars = static_cast<const uint8_t *>(d_scalars_v);
-    if (pre && (n != table->n || scalar_size != 32 || n > MSM_MAX_BATCH)) { ctx->err = "msm: table geometry mismatch"; return B200_ERR_ARG; }
+    if (pre && (n != table->n || scalar_size != 32 || n > MSM_MAX_BATCH || (ctx->opt_max_batch_log2 >= 4 && n > (1ull << ctx->opt_max_batch_log2)))) { ctx->err = "msm: table geometry mismatch"; return B200_ERR_ARG; }
 
-    const u32 batch_max = n < MSM_MAX_BATCH ? (u32)n : MSM_MAX_BATCH;
+    const u32 batch_cap = (ctx->opt_max_batch_log2 >= 4 && ctx->opt_max_batch_log2 <= 24) ? (1u << ctx->opt_max_batch_log2) : MSM_MAX_BATCH;
+    const u32 batch_max = n < batch_cap ? (u32)n : batch_cap;
     int c = pre ? table->c : msm_auto_c(n);
     if (!pre && ctx->force_c >= 4 && ctx->force_c <= 20) c = ctx->force_c;
     MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre, ctx->opt_target_tasks_log2, tail);
