@@ -40,5 +40,20 @@ public:
 
 std::unique_ptr<BinFile> openExisting(std::string filename, std::string type, uint32_t maxVersion);
 
+// Scoped sequential reader of one section (startReadSection ... endReadSection with the size check).
+class SectionReader {
+    BinFile *f;
+    bool open;
+
+public:
+    SectionReader(BinFile *file, uint32_t sectionId, uint32_t sectionPos = 0) : f(file), open(true) { f->startReadSection(sectionId, sectionPos); }
+    ~SectionReader() { if (open) f->endReadSection(false); }
+    uint32_t u32() { return f->readU32LE(); }
+    uint64_t u64() { return f->readU64LE(); }
+    void *raw(uint64_t len) { return f->read(len); }
+    std::vector<uint8_t> bytes(uint64_t len) { const uint8_t *p = (const uint8_t *)f->read(len); return std::vector<uint8_t>(p, p + len); }
+    void finish() { open = false; f->endReadSection(true); }
+};
+
 }  // namespace BinFileUtils
 #endif

@@ -33,13 +33,14 @@ static std::string jsonEscape(const std::string &s) {
 FullProver::FullProver(std::string zkeyFileNames[], int size) : status(uninitialized), canceled(false) {
     for (int i = 0; i < size; i++) {
         std::string circuit = getfilename(zkeyFileNames[i]);
-        zKeys[circuit] = BinFileUtils::openExisting(zkeyFileNames[i], "zkey", 1);
-        zkHeaders[circuit] = ZKeyUtils::loadHeader(zKeys[circuit].get());
-        auto &h = zkHeaders[circuit];
+        Circuit &ck = circuits[circuit];
+        ck.file = BinFileUtils::openExisting(zkeyFileNames[i], "zkey", 1);
+        ck.header = ZKeyUtils::loadHeader(ck.file.get());
+        auto &h = ck.header;
         if (h->n8r != 32 || memcmp(h->rPrime.data(), AltBn128::kFrPrime, 32) != 0)
             throw std::invalid_argument("zkey curve not supported");
-        auto &z = zKeys[circuit];
-        provers[circuit] = Groth16::makeProver<AltBn128::Engine>(
+        auto &z = ck.file;
+        ck.prover = Groth16::makeProver<AltBn128::Engine>(
             h->nVars, h->nPublic, h->domainSize, h->nCoefs, h->vk_alpha1, h->vk_beta1, h->vk_beta2, h->vk_delta1,
             h->vk_delta2, z->getSectionData(4), z->getSectionData(5), z->getSectionData(6), z->getSectionData(7),
             z->getSectionData(8), z->getSectionData(9));
@@ -83,7 +84,9 @@ void FullProver::checkPending() {
 void FullProver::thread_calculateProve() {
     try {
         std::string circuit = executingCircuit;
-        if (provers.find(circuit) == provers.end()) throw std::runtime_error("unknown circuit: " + circuit);
+        auto it = circuits.find(circuit);
+        if (it == circuits.end()) throw std::runtime_error("unknown circuit: " + circuit);
+        Circuit &ck = it->second;
         {
             std::ofstream file("./build/input_" + circuit + ".json");
             file << executingInput;
@@ -110,17 +113,17 @@ void FullProver::thread_calculateProve() {
         if (wtnsHeader->n8 != 32 || memcmp(wtnsHeader->prime.data(), AltBn128::kFrPrime, 32) != 0)
             throw std::runtime_error("different wtns curve");
         AltBn128::FrElement *wtnsData = (AltBn128::FrElement *)wtns->getSectionData(2);
-        if (wtns->getSectionSize(2) < (uint64_t)zkHeaders[circuit]->nVars * 32) throw std::runtime_error("witness too short for this zkey");
+        if (wtns->getSectionSize(2) < (uint64_t)ck.header->nVars * 32) throw std::runtime_error("witness too short for this zkey");
 
         std::string pd = "[";
-        for (uint32_t i = 1; i <= zkHeaders[circuit]->nPublic; i++) {
+        for (uint32_t i = 1; i <= ck.header->nPublic; i++) {
             if (i > 1) pd += ",";
             pd += "\"" + AltBn128::le32ToString(&wtnsData[i]) + "\"";
         }
         pd += "]";
         pubData = pd;
 
-        if (!isCanceled()) proof = provers[circuit]->prove(wtnsData)->toJson();
+        if (!isCanceled()) proof = ck.prover->prove(wtnsData)->toJson();
         else proof = "null";
         calcFinished();
     } catch (std::runtime_error &e) {

@@ -13,25 +13,6 @@
 #include "zkey_utils.hpp"
 
 class FullProver {
-    enum Status { aborted = -2, busy = -1, failed = 0, success = 1, unverified = 2, uninitialized = 3, initializing = 5, ready = 6 };
-    Status status;
-    std::mutex mtx;
-
-    std::string pendingInput, executingInput, pendingCircuit, executingCircuit;
-    std::map<std::string, std::unique_ptr<Groth16::Prover<AltBn128::Engine>>> provers;
-    std::map<std::string, std::unique_ptr<ZKeyUtils::Header>> zkHeaders;
-    std::map<std::string, std::unique_ptr<BinFileUtils::BinFile>> zKeys;
-
-    std::string proof;    // compact JSON text
-    std::string pubData;  // compact JSON text
-    std::string errString;
-    bool canceled;
-
-    bool isCanceled();
-    void calcFinished();
-    void thread_calculateProve();
-    void checkPending();   // mtx held
-
 public:
     FullProver(std::string zkeyFileNames[], int size);
     ~FullProver();
@@ -39,5 +20,29 @@ public:
     void abort();
     std::string getStatus();   // {"status":"success","proof":"<json text>","pubData":"<json text>"} etc.
     std::string &getErrString() { return errString; }
+
+private:
+    // same state machine as the reference (fullprover.hpp:14)
+    enum Status { aborted = -2, busy = -1, failed = 0, success = 1, unverified = 2, uninitialized = 3, initializing = 5, ready = 6 };
+
+    struct Circuit {            // one resident zkey: file mapping, parsed header, GPU prover
+        std::unique_ptr<BinFileUtils::BinFile> file;
+        std::unique_ptr<ZKeyUtils::Header> header;
+        std::unique_ptr<Groth16::Prover<AltBn128::Engine>> prover;
+    };
+    std::map<std::string, Circuit> circuits;
+
+    std::mutex mtx;
+    Status status;
+    bool canceled;
+    std::string pendingInput, pendingCircuit;       // latest request, not started yet
+    std::string executingInput, executingCircuit;   // request being proved by the worker thread
+    std::string proof, pubData;                     // compact JSON texts of the last result
+    std::string errString;
+
+    void checkPending();            // mtx held: start the worker if idle and a request is pending
+    void thread_calculateProve();   // worker: witness (popen) -> prove -> calcFinished
+    void calcFinished();
+    bool isCanceled();
 };
 #endif

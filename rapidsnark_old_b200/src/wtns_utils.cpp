@@ -2,15 +2,15 @@
 
 namespace WtnsUtils {
 
+// wtns section 1: u32 n8 | prime (n8 bytes, little-endian) | u32 nVars   (reference: wtns_utils.cpp:12-25)
 std::unique_ptr<Header> loadHeader(BinFileUtils::BinFile *f) {
-    std::unique_ptr<Header> h(new Header());
-    f->startReadSection(1);
-    h->n8 = f->readU32LE();
-    const uint8_t *p = (const uint8_t *)f->read(h->n8);
-    h->prime.assign(p, p + h->n8);
-    h->nVars = f->readU32LE();
-    f->endReadSection();
-    return h;
+    BinFileUtils::SectionReader rd(f, 1);
+    auto hdr = std::make_unique<Header>();
+    hdr->n8 = rd.u32();
+    hdr->prime = rd.bytes(hdr->n8);
+    hdr->nVars = rd.u32();
+    rd.finish();
+    return hdr;
 }
 
 }  // namespace WtnsUtils

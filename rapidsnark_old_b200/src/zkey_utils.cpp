@@ -3,33 +3,33 @@
 
 namespace ZKeyUtils {
 
+// Sections read (reference: zkey_utils.cpp:17-52): 1 = protocol id (1 = groth16); 2 = field sizes and primes,
+// circuit dimensions and the verification-key points; the coefficient count comes from the size of section 4.
 std::unique_ptr<Header> loadHeader(BinFileUtils::BinFile *f) {
-    std::unique_ptr<Header> h(new Header());
-    f->startReadSection(1);
-    uint32_t protocol = f->readU32LE();
-    if (protocol != 1) throw std::invalid_argument("zkey file is not groth16");
-    f->endReadSection();
-
-    f->startReadSection(2);
-    h->n8q = f->readU32LE();
-    const uint8_t *q = (const uint8_t *)f->read(h->n8q);
-    h->qPrime.assign(q, q + h->n8q);
-    h->n8r = f->readU32LE();
-    const uint8_t *r = (const uint8_t *)f->read(h->n8r);
-    h->rPrime.assign(r, r + h->n8r);
-    h->nVars = f->readU32LE();
-    h->nPublic = f->readU32LE();
-    h->domainSize = f->readU32LE();
-    h->vk_alpha1 = f->read(h->n8q * 2);
-    h->vk_beta1 = f->read(h->n8q * 2);
-    h->vk_beta2 = f->read(h->n8q * 4);
-    h->vk_gamma2 = f->read(h->n8q * 4);
-    h->vk_delta1 = f->read(h->n8q * 2);
-    h->vk_delta2 = f->read(h->n8q * 4);
-    f->endReadSection();
-
-    h->nCoefs = f->getSectionSize(4) / (12 + h->n8r);
-    return h;
+    {
+        BinFileUtils::SectionReader proto(f, 1);
+        if (proto.u32() != 1) throw std::invalid_argument("zkey file is not groth16");
+        proto.finish();
+    }
+    auto hdr = std::make_unique<Header>();
+    BinFileUtils::SectionReader rd(f, 2);
+    hdr->n8q = rd.u32();
+    hdr->qPrime = rd.bytes(hdr->n8q);
+    hdr->n8r = rd.u32();
+    hdr->rPrime = rd.bytes(hdr->n8r);
+    hdr->nVars = rd.u32();
+    hdr->nPublic = rd.u32();
+    hdr->domainSize = rd.u32();
+    const uint64_t g1 = (uint64_t)hdr->n8q * 2, g2 = (uint64_t)hdr->n8q * 4;   // affine point sizes
+    hdr->vk_alpha1 = rd.raw(g1);
+    hdr->vk_beta1 = rd.raw(g1);
+    hdr->vk_beta2 = rd.raw(g2);
+    hdr->vk_gamma2 = rd.raw(g2);
+    hdr->vk_delta1 = rd.raw(g1);
+    hdr->vk_delta2 = rd.raw(g2);
+    rd.finish();
+    hdr->nCoefs = f->getSectionSize(4) / (12 + hdr->n8r);   // 44-byte records; the leading u32 count is slack
+    return hdr;
 }
 
 }  // namespace ZKeyUtils
