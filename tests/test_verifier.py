@@ -61,3 +61,34 @@ def test_gpu_proof_with_random_blinding_verifies():
     zk.free()
     ctx.close()
     assert pairing.groth16_verify(vk, proof, public)
+
+
+def test_config1_reference_cli_2_10_proof_verifies(tmp_path):
+    """BASELINE.json configs[0]: 2^10-constraint synthetic zkey + wtns -> the reference's own CPU prover
+    (oracle/_ref/ref_prover = src/main_prover.cpp compiled from /root/reference) -> proof.json / public.json ->
+    native pairing verification with the verification key exported from the zkey (tools/export_vkey.py)."""
+    import subprocess
+    import sys
+    import synth_util
+    from rapidsnark_old_b200 import synth
+    ref_prover = os.path.join(ROOT, "oracle", "_ref", "ref_prover")
+    if not os.path.exists(ref_prover):
+        pytest.skip("oracle/_ref/ref_prover not built")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import export_vkey
+    s = synth_util.make(10)
+    zk, wt = tmp_path / "c.zkey", tmp_path / "w.wtns"
+    zk.write_bytes(synth.zkey_bytes(s))
+    wt.write_bytes(synth.wtns_bytes_file(s))
+    subprocess.check_call([ref_prover, str(zk), str(wt), str(tmp_path / "proof.json"), str(tmp_path / "public.json")],
+                          cwd=tmp_path)
+    vkj = export_vkey.export(zk.read_bytes())
+    assert vkj["nPublic"] == 4 and len(vkj["IC"]) == 5
+    g1 = lambda p: (int(p[0]), int(p[1]))
+    g2 = lambda p: ((int(p[0][0]), int(p[0][1])), (int(p[1][0]), int(p[1][1])))
+    vk = {"alpha1": g1(vkj["vk_alpha_1"]), "beta2": g2(vkj["vk_beta_2"]), "gamma2": g2(vkj["vk_gamma_2"]),
+          "delta2": g2(vkj["vk_delta_2"]), "IC": [g1(p) for p in vkj["IC"]]}
+    proof = _proof_from_json((tmp_path / "proof.json").read_text())
+    public = [int(x) for x in json.loads((tmp_path / "public.json").read_text())]
+    assert public == s.wtns[1:5]
+    assert pairing.groth16_verify(vk, proof, public)
