@@ -71,6 +71,10 @@ Prover<Engine>::Prover(uint32_t _nVars, uint32_t _nPublic, uint32_t _domainSize,
             gpus.clear();
             throw std::runtime_error(msg);
         }
+        // B200_PRECOMP=0|1 / B200_PRECOMP_C=<bits>: per-window tables on/off (on by default: they pay off from the
+        // second proof on; the one-shot CLI turns them off itself)
+        if (const char *e = getenv("B200_PRECOMP")) b200_set_option(gp.ctx, "precomp", atoi(e));
+        if (const char *e = getenv("B200_PRECOMP_C")) b200_set_option(gp.ctx, "precomp_c", atoi(e));
         b200_zkey_desc d;
         d.n_vars = nVars; d.n_public = nPublic; d.domain_size = domainSize; d.n_coefs = nCoefs;
         d.coefs = coefs; d.points_a = pointsA; d.points_b1 = pointsB1; d.points_b2 = pointsB2;

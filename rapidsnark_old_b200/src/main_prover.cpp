@@ -3,6 +3,7 @@
 // Extras, all optional and via the environment: B200_GPUS=N (shard the MSMs over N GPUs of this box),
 // B200_DEVICE=i (first GPU), B200_TIMING=1 (phase timings to stderr), B200_R / B200_S (hex, test only:
 // fixed blinding factors), B200_DUMP_MSMS=file (the five pre-blinding MSM results, 768 bytes).
+#include <stdlib.h>
 #include <string.h>
 #include <chrono>
 #include <fstream>
@@ -46,6 +47,7 @@ int main(int argc, char **argv) {
         if (wtnsHeader->n8 != 32 || memcmp(wtnsHeader->prime.data(), AltBn128::kFrPrime, 32) != 0)
             throw std::invalid_argument("different wtns curve");
         auto t1 = clk::now();
+        setenv("B200_PRECOMP", "0", 0);   // one proof per process: building per-window tables would cost more than it saves
         auto prover = Groth16::makeProver<AltBn128::Engine>(
             zkeyHeader->nVars, zkeyHeader->nPublic, zkeyHeader->domainSize, zkeyHeader->nCoefs, zkeyHeader->vk_alpha1,
             zkeyHeader->vk_beta1, zkeyHeader->vk_beta2, zkeyHeader->vk_delta1, zkeyHeader->vk_delta2,

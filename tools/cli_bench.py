@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""End-to-end CLI comparison at full size (BASELINE.json configs[1], "CLI wall-clock incl. file read + H2D"):
+writes the synthetic 2^k zkey / wtns files, runs the reference CLI (oracle/_ref/ref_prover, built from
+/root/reference/src/main_prover.cpp) and build/prover on them with the SAME blinding factors, and checks that
+proof.json and public.json are byte-identical.  Prints one JSON line with both wall-clock times.
+    python tools/cli_bench.py --log-n 20 [--gpus 1]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import rapidsnark_old_b200 as b200
+from rapidsnark_old_b200 import synth
+import bench
+from make_golden import fixed_rs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--skip-reference", action="store_true")
+    args = ap.parse_args()
+    ctx = b200.Context(0)
+    s = bench.build_inputs(args.log_n, 2, *bench.gpu_point_makers(ctx))
+    ctx.close()
+    d = tempfile.mkdtemp(prefix="b200cli")
+    zk, wt = os.path.join(d, "c.zkey"), os.path.join(d, "w.wtns")
+    open(zk, "wb").write(synth.zkey_bytes(s))
+    open(wt, "wb").write(synth.wtns_bytes_file(s))
+    seed = "5eed"
+    rb, sb = fixed_rs(seed, 1), fixed_rs(seed, 2)
+    out = {"log_n": args.log_n, "zkey_mb": round(os.path.getsize(zk) / 1e6, 1)}
+    env = dict(os.environ, B200_R=rb[::-1].hex(), B200_S=sb[::-1].hex(), B200_TIMING="1", B200_GPUS=str(args.gpus))
+    for rep in range(2):                        # second run: page cache warm, like the reference run below
+        t = time.perf_counter()
+        r = subprocess.run([os.path.join(ROOT, "build", "prover"), zk, wt, os.path.join(d, "p1.json"), os.path.join(d, "pub1.json")],
+                           env=env, capture_output=True, text=True)
+        out["b200_cli_wall_s"] = round(time.perf_counter() - t, 3)
+        assert r.returncode == 0, r.stderr
+    out["b200_cli_phases"] = r.stderr.strip().splitlines()[0]
+    if not args.skip_reference:
+        t = time.perf_counter()
+        subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_prover"), zk, wt, os.path.join(d, "p2.json"),
+                               os.path.join(d, "pub2.json")], env=dict(os.environ, ORACLE_FIXED_RS=seed), cwd=d)
+        out["reference_cli_wall_s"] = round(time.perf_counter() - t, 3)
+        out["proof_json_identical"] = open(os.path.join(d, "p1.json")).read() == open(os.path.join(d, "p2.json")).read()
+        out["public_json_identical"] = open(os.path.join(d, "pub1.json")).read() == open(os.path.join(d, "pub2.json")).read()
+    print(json.dumps(out), flush=True)
+    if not args.skip_reference:
+        assert out["proof_json_identical"] and out["public_json_identical"]
+
+
+if __name__ == "__main__":
+    main()
