@@ -29,7 +29,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "groth16_proof_ms_2^20_constraints"
+METRIC = "groth16_proof_ms_2^20_constraints"   # --log-n K renames it to ..._2^K_...
 UNIT = "ms"
 
 
@@ -356,6 +356,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3
+    global METRIC
+    METRIC = "groth16_proof_ms_2^%d_constraints" % args.log_n
     if args.impl == "reference":
         return run_reference(args)
     return run_own(args)

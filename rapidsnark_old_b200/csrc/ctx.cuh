@@ -64,7 +64,7 @@ struct Ctx {
     void *pinned = nullptr;            // small pinned host buffer for results
     size_t pinned_cap = 0;
 
-    struct SlotInfo { int nwin_b = 0, nwin = 0, c = 0; bool used = false; } slot_info[MSM_SLOTS];
+    struct SlotInfo { int nwin_b = 0, nwin = 0, c = 0, nplanes = 0, L = 0; bool used = false; } slot_info[MSM_SLOTS];
 
     // NTT twiddle tables (built lazily per log-size)
     struct Twiddles;
@@ -171,8 +171,9 @@ inline void phase_collect(Ctx *ctx) {  // both streams must be synchronized
     } while (0)
 
 void ntt_free_tables(Ctx *ctx);   // ntt.cu
-void host_horner_g1(const void *win, int nwin, int c, void *out);   // src/hostmath.cpp (g++)
-void host_horner_g2(const void *win, int nwin, int c, void *out);
+// src/hostmath.cpp (g++): planes[set][0..nplanes-1] = bit-plane sums of S, planes[set][nplanes] = sum of W
+void host_msm_finish_g1(const void *planes, int nsets, int nplanes, int L, int nwin, int c, void *out);
+void host_msm_finish_g2(const void *planes, int nsets, int nplanes, int L, int nwin, int c, void *out);
 
 // msm entry points implemented in msm_g1.cu / msm_g2.cu
 struct MsmTableRaw {        // resident per-window table 2^(c*j) * P_i (see msm.cuh); tbl == nullptr: none

@@ -20,10 +20,11 @@
 //                           Skewed witnesses (huge |digit| = 1 buckets) become many sub-tasks whose
 //                           partial sums are folded by k_msm_merge_hot (one CTA per hot bucket:
 //                           strided partial sums + shared-memory tree)
-//   6. k_msm_reduce_segments / k_msm_window_sum   sum_k k*B_k per window: running sums over
-//                           segments of L buckets + small in-thread multiplier, then a CTA tree
-//   7. host: Horner over the <= 65 window sums (a serial chain of ~270 group operations is ~8x
-//      faster on one CPU core than on one GPU thread)
+//   6. k_msm_reduce_segments / k_msm_plane_sum / k_msm_window_sum   sum_k k*B_k per bucket set:
+//                           running sums over segments of L buckets give (W_seg, S_seg); the weights
+//                           of the segment starts come from bit-plane sums of S over the segment index
+//   7. host: Horner over the <= 21 planes and <= 65 window sums (a serial chain of ~270 group
+//      operations is ~8x faster on one CPU core than on one GPU thread)
 //
 // Resident tables (zkey point sections are static): k_msm_precompute stores 2^(c*j) * P_i for every
 // window j next to the original points, once, at upload time.  All windows then share ONE bucket
@@ -49,6 +50,7 @@ struct MsmGeom {
     u32 CAP;        // max entries per accumulate task
     u32 L;          // buckets per reduce segment
     u32 nseg;       // segments per bucket set
+    u32 nplanes;    // ceil(log2(nseg)): bit planes of the segment index
 };
 
 static const u32 MSM_MAX_BATCH = 1u << 24;   // points per sort batch (entries < 2^32, entry index < 2^31)
@@ -60,9 +62,9 @@ static const u32 MSM_MAX_CAP = 2048;         // task-length histogram has MSM_MA
 inline int msm_auto_c(uint64_t n) {
     int lg = 0;
     while ((2ull << lg) <= n) lg++;   // floor(log2 n)
-    int c = lg - 5;                   // measured on B200: 2^20 points -> c = 14..15
+    int c = lg - 5;                   // measured on B200: 2^20 points -> c = 15..16, 2^24 -> 19
     if (c < 4) c = 4;
-    if (c > 16) c = 16;
+    if (c > 20) c = 20;
     return c;
 }
 
@@ -89,6 +91,8 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     g.L = g.nbk >= (1u << 18) ? 64 : g.nbk >= (1u << 17) ? 32 : g.nbk >= 16 ? 16 : g.nbk;
     if (tail && g.L > 16) g.L = 16;   // nothing left to overlap with: shortest chains, the whole GPU is free
     g.nseg = g.nbk / g.L;
+    g.nplanes = 0;
+    while ((1u << g.nplanes) < g.nseg) g.nplanes++;
     return g;
 }
 
@@ -430,13 +434,38 @@ __global__ void __launch_bounds__(128, 3) k_msm_reduce_segments(const Xyzz<F> *_
         ec_add(run, q);
         ec_add(acc, run);
     }
-    // acc = sum (k+1) B_k over the segment; the segment starts at bucket s*L, so add (s*L) * run
-    u32 mult = s * L;
-    if (mult != 0 && !run.is_zero()) {
-        Xyzz<F> m = ec_mul(run, &mult, 1);
-        ec_add(acc, m);
+    // acc = sum (k+1) B_k over the segment (local weights), run = plain sum.  The segment starts at bucket s*L:
+    // its true contribution is acc + (s*L) * run; the second term is assembled from bit-plane sums of `run`
+    // over the segment index (k_msm_plane_sum) instead of a per-thread scalar multiplication.
+    st_struct(seg_out + 2 * (size_t)g, acc);
+    st_struct(seg_out + 2 * (size_t)g + 1, run);
+}
+
+// Bit-plane sums over the segments of one bucket set: CTA (chunk, plane, set).
+//   plane t < nplanes : sum of S_seg over the chunk's segments whose index has bit t set
+//   plane == nplanes  : sum of W_seg over the chunk's segments
+// out[(set * (nplanes + 1) + plane) * nchunk + chunk].  sum_seg seg * S_seg = sum_t 2^t * plane_t.
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_plane_sum(const Xyzz<F> *__restrict__ segs, u32 nseg, u32 nchunk, u32 nplanes,
+                                                         Xyzz<F> *__restrict__ out) {
+    extern __shared__ uint4 smem_raw[];
+    Xyzz<F> *sm = reinterpret_cast<Xyzz<F> *>(smem_raw);
+    const u32 chunk = blockIdx.x, plane = blockIdx.y, w = blockIdx.z;
+    const u32 per = (nseg + nchunk - 1) / nchunk;
+    const u32 lo = chunk * per, hi = (lo + per < nseg) ? lo + per : nseg;
+    const Xyzz<F> *base = segs + 2 * (size_t)w * nseg;
+    Xyzz<F> acc = Xyzz<F>::zero();
+    for (u32 s = lo + threadIdx.x; s < hi; s += blockDim.x) {
+        if (plane == nplanes) {
+            Xyzz<F> q = ld_struct(base + 2 * (size_t)s);
+            ec_add(acc, q);
+        } else if ((s >> plane) & 1u) {
+            Xyzz<F> q = ld_struct(base + 2 * (size_t)s + 1);
+            ec_add(acc, q);
+        }
     }
-    st_struct(seg_out + g, acc);
+    cta_tree_sum(acc, sm);
+    if (threadIdx.x == 0) st_struct(out + ((size_t)w * (nplanes + 1) + plane) * nchunk + chunk, acc);
 }
 
 // plain sums: CTA (chunk, set) adds its slice of the set's nitems points; out[set * nchunk + chunk]
@@ -554,9 +583,12 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     B200_TRY(ctx_reserve(ctx, ctx->w_hot, ((size_t)3 * g.NB + 8) * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_plan, (size_t)(2 * SCAN_TILE + 16) * 4));
     B200_TRY(ctx_reserve(ctx, ctx->w_tasks, max_tasks * sizeof(uint2)));
-    B200_TRY(ctx_reserve(ctx, ctx->w_segs[bb], ((size_t)total_segs + 128 * g.nwin_b) * PT_MAX));
-    B200_TRY(ctx_reserve(ctx, ctx->w_win, (size_t)Ctx::MSM_SLOTS * MSM_MAX_WIN * PT_MAX));
-    B200_TRY(ctx_pinned(ctx, (size_t)Ctx::MSM_SLOTS * MSM_MAX_WIN * PT_MAX));
+    const u32 npl1 = g.nplanes + 1;
+    const size_t MSM_SLOT_PTS = 512;   // (planes + 1) x bucket sets per result slot
+    if ((size_t)npl1 * g.nwin_b > MSM_SLOT_PTS) { ctx->err = "msm: too many window x plane sums"; return B200_ERR_ARG; }
+    B200_TRY(ctx_reserve(ctx, ctx->w_segs[bb], (2 * (size_t)total_segs + (size_t)128 * npl1 * g.nwin_b) * PT_MAX));
+    B200_TRY(ctx_reserve(ctx, ctx->w_win, (size_t)Ctx::MSM_SLOTS * MSM_SLOT_PTS * PT_MAX));
+    B200_TRY(ctx_pinned(ctx, (size_t)Ctx::MSM_SLOTS * MSM_SLOT_PTS * PT_MAX));
 
     u32 *d_hist = (u32 *)ctx->w_hist.p, *d_cursor = (u32 *)ctx->w_cursor.p, *d_totals = (u32 *)ctx->w_scan_totals.p;
     u32 *d_entries = (u32 *)ctx->w_entries.p;
@@ -566,8 +598,8 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     uint2 *d_tasks = (uint2 *)ctx->w_tasks.p;
     Pt *d_buckets = (Pt *)ctx->w_buckets[bb].p, *d_partial = (Pt *)ctx->w_partial[bb].p;
     Pt *d_segs = (Pt *)ctx->w_segs[bb].p;
-    Pt *d_win = (Pt *)((uint8_t *)ctx->w_win.p + (size_t)slot * MSM_MAX_WIN * PT_MAX);
-    Pt *h_win = (Pt *)((uint8_t *)ctx->pinned + (size_t)slot * MSM_MAX_WIN * PT_MAX);
+    Pt *d_win = (Pt *)((uint8_t *)ctx->w_win.p + (size_t)slot * MSM_SLOT_PTS * PT_MAX);
+    Pt *h_win = (Pt *)((uint8_t *)ctx->pinned + (size_t)slot * MSM_SLOT_PTS * PT_MAX);
     cudaStream_t st = ctx->stream, side = ctx->side[slot];
     const bool g2 = sizeof(F) != 32;
     const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
@@ -643,18 +675,18 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     phase_begin(ctx, PH_MSM_REDUCE, side);
     B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 31) / 32, 32, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
     {
-        // window sums in two passes: nchunk CTAs per bucket set, then one CTA per set over the chunk sums
+        // plane sums in two passes: nchunk CTAs per (set, plane), then one CTA per (set, plane) over the chunk sums
         u32 nchunk = (g.nseg + 1023) / 1024;
         if (nchunk > 128) nchunk = 128;
-        Pt *d_chunk = d_segs + total_segs;
-        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(nchunk, g.nwin_b), 128, 128 * sizeof(Pt), d_segs, g.nseg, nchunk, d_chunk);
-        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, g.nwin_b), 128, 128 * sizeof(Pt), d_chunk, nchunk, 1u, d_win);
+        Pt *d_chunk = d_segs + 2 * (size_t)total_segs;
+        B200_LAUNCH_ON(ctx, side, k_msm_plane_sum<F>, dim3(nchunk, npl1, g.nwin_b), 128, 128 * sizeof(Pt), d_segs, g.nseg, nchunk, g.nplanes, d_chunk);
+        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, npl1 * g.nwin_b), 128, 128 * sizeof(Pt), d_chunk, nchunk, 1u, d_win);
     }
     phase_end(ctx, side);
-    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * sizeof(Pt), cudaMemcpyDeviceToHost, side));
+    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * npl1 * sizeof(Pt), cudaMemcpyDeviceToHost, side));
     B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_done[slot], side));
     ctx->slot_busy[slot] = true;
-    si.nwin_b = (int)g.nwin_b; si.nwin = g.nwin; si.c = g.c; si.used = true;
+    si.nwin_b = (int)g.nwin_b; si.nwin = g.nwin; si.c = g.c; si.nplanes = (int)g.nplanes; si.L = (int)g.L; si.used = true;
     return B200_OK;
 }
 
@@ -667,11 +699,11 @@ int msm_collect_impl(Ctx *ctx, int slot, Xyzz<F> *out_host) {
     if (si.nwin_b == 0) { *out_host = Pt::zero(); return B200_OK; }
     B200_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev_done[slot]));
     ctx->slot_busy[slot] = false;
-    const Pt *h_win = (const Pt *)((const uint8_t *)ctx->pinned + (size_t)slot * MSM_MAX_WIN * sizeof(G2Xyzz));
-    // Horner over the windows (multiexp.cpp:137-141) on the host's 4x64 field
-    if (si.nwin_b == 1) *out_host = h_win[0];
-    else if (sizeof(F) == 32) host_horner_g1(h_win, si.nwin, si.c, out_host);
-    else host_horner_g2(h_win, si.nwin, si.c, out_host);
+    const Pt *h_win = (const Pt *)((const uint8_t *)ctx->pinned + (size_t)slot * 512 * sizeof(G2Xyzz));
+    // per bucket set: W + L * sum_t 2^t plane_t, then Horner over the windows (multiexp.cpp:137-141), all on the
+    // host's 4x64 field
+    if (sizeof(F) == 32) host_msm_finish_g1(h_win, si.nwin_b, si.nplanes, si.L, si.nwin, si.c, out_host);
+    else host_msm_finish_g2(h_win, si.nwin_b, si.nplanes, si.L, si.nwin, si.c, out_host);
     return B200_OK;
 }
 

@@ -17,9 +17,29 @@ template <class T> void st(void *p, const T &t) { memcpy(p, &t, sizeof(T)); }
 }
 
 namespace b200 {
-// window Horner of the MSM (multiexp.cpp:137-141) on the fast 4x64 host field; called from msm.cuh
-void host_horner_g1(const void *win, int nwin, int c, void *out) { horner<HFq>((const Xyzz<HFq> *)win, nwin, c, (Xyzz<HFq> *)out); }
-void host_horner_g2(const void *win, int nwin, int c, void *out) { horner<HFq2>((const Xyzz<HFq2> *)win, nwin, c, (Xyzz<HFq2> *)out); }
+// Host end of the MSM (called from msm.cuh): per bucket set  T = W + L * sum_t 2^t * plane_t,  then the window
+// Horner of multiexp.cpp:137-141 when the sets are windows (one set = resident per-window tables, nothing to do).
+template <class F>
+static void msm_finish(const Xyzz<F> *planes, int nsets, int nplanes, int L, int nwin, int c, Xyzz<F> *out) {
+    Xyzz<F> total = Xyzz<F>::zero();
+    for (int w = nsets - 1; w >= 0; w--) {
+        const Xyzz<F> *p = planes + (size_t)w * (nplanes + 1);
+        Xyzz<F> t = Xyzz<F>::zero();
+        for (int k = nplanes - 1; k >= 0; k--) { t = ec_dbl(t); ec_add(t, p[k]); }
+        for (int l = L; l > 1; l >>= 1) t = ec_dbl(t);
+        ec_add(t, p[nplanes]);
+        if (nsets > 1) for (int k = 0; k < c; k++) total = ec_dbl(total);
+        ec_add(total, t);
+    }
+    (void)nwin;
+    *out = total;
+}
+void host_msm_finish_g1(const void *planes, int nsets, int nplanes, int L, int nwin, int c, void *out) {
+    msm_finish<HFq>((const Xyzz<HFq> *)planes, nsets, nplanes, L, nwin, c, (Xyzz<HFq> *)out);
+}
+void host_msm_finish_g2(const void *planes, int nsets, int nplanes, int L, int nwin, int c, void *out) {
+    msm_finish<HFq2>((const Xyzz<HFq2> *)planes, nsets, nplanes, L, nwin, c, (Xyzz<HFq2> *)out);
+}
 
 // Blinding + finalisation of src/groth16.cpp:209-253 with explicit r, s (32-byte little-endian, used
 // un-reduced like the reference's 248-bit values): in = pih, pi_a, pib1 (G1 XYZZ), pi_b (G2 XYZZ), pi_c.
