@@ -239,6 +239,87 @@ HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
     return r;
 }
 
+// ---- separated product / reduction (used by the lazily reduced Fq2 product in fq2.cuh) ----------------------
+namespace detail {
+
+// t[0..15] = a[0..7] * b[0..7], plain 512-bit product.  Same even/odd accumulator idea as mont_round: E holds the
+// 64-bit partial products whose low word sits at an even position, O those at odd positions (O[k] = position
+// k+1), so every product is one IMAD.WIDE with an aligned addend; the two are added once at the end.
+HD void mul8x8(u32 *t, const u32 *a, const u32 *b) {
+    u32 E[16], O[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u32 bi = b[i];
+        // even limbs of a: first pair at position i; odd limbs: first pair at position i + 1
+        u32 *Xe = (i & 1) ? O : E;
+        const int se = (i & 1) ? i - 1 : i;
+        u32 *Xo = (i & 1) ? E : O;
+        const int so = (i & 1) ? i + 1 : i;
+        Xe[se] = mad_lo_cc(a[0], bi, Xe[se]);
+        Xe[se + 1] = madc_hi_cc(a[0], bi, Xe[se + 1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            Xe[se + j] = madc_lo_cc(a[j], bi, Xe[se + j]);
+            Xe[se + j + 1] = madc_hi_cc(a[j], bi, Xe[se + j + 1]);
+        }
+        if (se + 8 < 16) Xe[se + 8] = addc(Xe[se + 8], 0);
+        Xo[so] = mad_lo_cc(a[1], bi, Xo[so]);
+        Xo[so + 1] = madc_hi_cc(a[1], bi, Xo[so + 1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            Xo[so + j] = madc_lo_cc(a[j + 1], bi, Xo[so + j]);
+            Xo[so + j + 1] = madc_hi_cc(a[j + 1], bi, Xo[so + j + 1]);
+        }
+        if (so + 8 < 16) Xo[so + 8] = addc(Xo[so + 8], 0);
+    }
+    t[0] = E[0];
+    t[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 15; k++) t[k] = addc_cc(E[k], O[k - 1]);
+    t[15] = addc(E[15], O[14]);
+}
+
+// Montgomery reduction of a 16-limb value t < p * 2^256: r = t * 2^-256 mod p, r < 2p before the final
+// conditional subtraction done by the caller.  Only the low half needs the m_i * p rounds; the high half is
+// added at the end (t_hi < p, reduced low half <= p).
+template <class P>
+HD void mont_reduce16(u32 *r, const u32 *t) {
+    u32 mod[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) mod[i] = P::mod(i);
+    u32 ev[8], od[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ev[i] = t[i];
+    {
+        u32 m = ev[0] * P::INV;
+        mul_pairs(od, mod + 1, m);
+        mad_pairs_cc(ev, mod, m);
+        od[7] = addc(od[7], 0);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        u32 *lo = (i & 1) ? od : ev;      // roles swap every round (see mont_round)
+        u32 *pend = (i & 1) ? ev : od;
+        lo[0] = add_cc(lo[0], pend[1]);
+        u32 m = lo[0] * P::INV;
+        mad_pairs_shift(pend, mod + 1, m);
+        mad_pairs_cc(lo, mod, m);
+        pend[7] = addc(pend[7], 0);
+    }
+    r[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r[i] = addc_cc(ev[i], od[i + 1]);
+    r[7] = addc(ev[7], 0);
+    r[0] = add_cc(r[0], t[8]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r[i] = addc_cc(r[i], t[8 + i]);
+    r[7] = addc(r[7], t[15]);
+}
+
+}  // namespace detail
+
 template <class P>
 HD Fp<P> fp_sqr(const Fp<P> &a) {
     return fp_mul(a, a);

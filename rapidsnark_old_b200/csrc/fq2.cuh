@@ -50,6 +50,50 @@ HD Fq2T<B> fmul(const Fq2T<B> &x, const Fq2T<B> &y) {
     return r;
 }
 
+// Device representation: lazily reduced product - three plain 512-bit products, the Karatsuba combination on the
+// unreduced values, then TWO Montgomery reductions instead of three (320 instead of 390 wide multiplies).
+//   c0 = a0 b0 - a1 b1   (+ p * 2^256 when negative, so that 0 <= c0 < p * 2^256)
+//   c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1 = a0 b1 + a1 b0 < 2 p^2 < p * 2^256
+// The sums a0 + a1, b0 + b1 stay unreduced (< 2p < 2^255 fits the 8 limbs).  Results are canonical like fp_mul's.
+HD Fq2T<Fq> fmul(const Fq2T<Fq> &x, const Fq2T<Fq> &y) {
+    u32 t0[16], t1[16], t2[16], sa[8], sb[8];
+    detail::mul8x8(t0, x.a.v, y.a.v);
+    detail::mul8x8(t1, x.b.v, y.b.v);
+    sa[0] = add_cc(x.a.v[0], x.b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) sa[i] = addc_cc(x.a.v[i], x.b.v[i]);
+    sa[7] = addc(x.a.v[7], x.b.v[7]);
+    sb[0] = add_cc(y.a.v[0], y.b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) sb[i] = addc_cc(y.a.v[i], y.b.v[i]);
+    sb[7] = addc(y.a.v[7], y.b.v[7]);
+    detail::mul8x8(t2, sa, sb);
+    // t2 -= t0; t2 -= t1   (never negative)
+    t2[0] = sub_cc(t2[0], t0[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) t2[i] = subc_cc(t2[i], t0[i]);
+    t2[15] = subc(t2[15], t0[15]);
+    t2[0] = sub_cc(t2[0], t1[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) t2[i] = subc_cc(t2[i], t1[i]);
+    t2[15] = subc(t2[15], t1[15]);
+    // t0 -= t1, add p * 2^256 back on borrow
+    t0[0] = sub_cc(t0[0], t1[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) t0[i] = subc_cc(t0[i], t1[i]);
+    u32 borrow = subc(0, 0);
+    t0[8] = add_cc(t0[8], borrow & FqParams::mod(0));
+#pragma unroll
+    for (int i = 1; i < 7; i++) t0[8 + i] = addc_cc(t0[8 + i], borrow & FqParams::mod(i));
+    t0[15] = addc(t0[15], borrow & FqParams::mod(7));
+    Fq2T<Fq> r;
+    detail::mont_reduce16<FqParams>(r.a.v, t0);
+    fp_reduce_once(r.a);
+    detail::mont_reduce16<FqParams>(r.b.v, t2);
+    fp_reduce_once(r.b);
+    return r;
+}
+
 // complex squaring, 2 base-field products (f2field.cpp:114-126)
 template <class B>
 HD Fq2T<B> fsqr(const Fq2T<B> &x) {
