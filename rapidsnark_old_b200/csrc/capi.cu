@@ -34,6 +34,10 @@ int b200_init(int device, b200_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_h, cudaEventDisableTiming);
+    for (int i = 0; i < Ctx::SORT_WS && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&h->c.ev_sort[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_ws_acc[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) {   // side streams (H pipeline; bucket folding / reduction): highest priority so their CTAs are
                               // placed as soon as an accumulation CTA retires instead of waiting for its grid to drain
         int lo_p = 0, hi_p = 0;
@@ -58,9 +62,14 @@ void b200_free(b200_ctx *h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) cudaStreamSynchronize(c->side[i]);
-    DevBuf *all[] = {&c->w_hist, &c->w_cursor, &c->w_entries, &c->w_hot, &c->w_scan_totals, &c->w_win, &c->w_plan,
-                     &c->w_tasks, &c->w_in_bases, &c->w_in_scalars, &c->w_ntt};
+    DevBuf *all[] = {&c->w_win, &c->w_in_bases, &c->w_in_scalars, &c->w_ntt};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < Ctx::SORT_WS; i++) {
+        DevBuf *ws[] = {&c->w_hist[i], &c->w_cursor[i], &c->w_entries[i], &c->w_hot[i], &c->w_scan_totals[i], &c->w_plan[i], &c->w_tasks[i]};
+        for (DevBuf *b : ws) if (b->p) cudaFree(b->p);
+        if (c->ev_sort[i]) cudaEventDestroy(c->ev_sort[i]);
+        if (c->ev_ws_acc[i]) cudaEventDestroy(c->ev_ws_acc[i]);
+    }
     for (int i = 0; i < Ctx::MSM_SLOTS; i++) {
         if (c->w_buckets[i].p) cudaFree(c->w_buckets[i].p);
         if (c->w_partial[i].p) cudaFree(c->w_partial[i].p);

@@ -40,7 +40,7 @@ struct Ctx {
                                                 // the next MSMs sort / accumulate on `stream`
     cudaEvent_t ev_acc[MSM_SLOTS] = {nullptr}, ev_done[MSM_SLOTS] = {nullptr}, ev_merge[MSM_SLOTS] = {nullptr};
     bool slot_busy[MSM_SLOTS] = {false};        // ev_done[slot] recorded and not yet waited for
-    unsigned sort_readers = 0;                  // slots whose side-stream merge reads the current sort workspace
+    unsigned sort_readers[2] = {0, 0};          // per sort workspace: slots whose side-stream merge still reads it
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -56,7 +56,11 @@ struct Ctx {
     std::vector<DevBuf *> bufs;  // everything to free
 
     // MSM workspaces (shared by G1/G2 calls; grow-only)
-    DevBuf w_hist, w_cursor, w_entries, w_buckets[MSM_SLOTS], w_partial[MSM_SLOTS], w_hot, w_scan_totals, w_segs[MSM_SLOTS], w_win, w_plan, w_tasks;
+    static const int SORT_WS = 2;       // independent sort workspaces (witness digits / h digits)
+    DevBuf w_hist[SORT_WS], w_cursor[SORT_WS], w_entries[SORT_WS], w_hot[SORT_WS], w_scan_totals[SORT_WS], w_plan[SORT_WS], w_tasks[SORT_WS];
+    DevBuf w_buckets[MSM_SLOTS], w_partial[MSM_SLOTS], w_segs[MSM_SLOTS], w_win;
+    cudaEvent_t ev_sort[SORT_WS] = {nullptr}, ev_ws_acc[SORT_WS] = {nullptr};
+    bool ws_acc_pending[SORT_WS] = {false, false};
     int opt_target_tasks_log2 = 0;     // 0 = default (msm.cuh)
     int opt_max_batch_log2 = 0;        // 0 = default 24; smaller values exercise the multi-batch path in tests
     DevBuf w_in_bases, w_in_scalars;   // staging for host-pointer calls
@@ -188,10 +192,13 @@ int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t sc
                const MsmTableRaw *table = nullptr);
 // asynchronous pair: enqueue all kernels of one MSM (result lands in pinned slot `slot`), collect = wait + host Horner
 // `tail`: no further MSM follows (nothing to overlap the bucket reduction with)
+// `ws`: sort workspace (0/1); `sort_stream`: run the digit sort there (e.g. behind the H pipeline) instead of ctx->stream
 int msm_g1_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
-                   const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true);
+                   const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true, int ws = 0,
+                   cudaStream_t sort_stream = nullptr);
 int msm_g2_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
-                   const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true);
+                   const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true, int ws = 0,
+                   cudaStream_t sort_stream = nullptr);
 int msm_g1_collect(Ctx *ctx, int slot, G1Xyzz *out_host);
 int msm_g2_collect(Ctx *ctx, int slot, G2Xyzz *out_host);
 int msm_g1_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl);

@@ -544,9 +544,9 @@ int msm_precompute_table(Ctx *ctx, const Affine<F> *d_pts, u32 n, int c, Affine<
 
 template <class F>
 int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint32_t scalar_size, uint64_t n, int slot,
-                     const MsmTable<F> *table, bool reuse_sort, bool tail) {
+                     const MsmTable<F> *table, bool reuse_sort, bool tail, int ws, cudaStream_t sort_stream) {
     typedef Xyzz<F> Pt;
-    if (slot < 0 || slot >= Ctx::MSM_SLOTS) { ctx->err = "msm: bad result slot"; return B200_ERR_ARG; }
+    if (slot < 0 || slot >= Ctx::MSM_SLOTS || ws < 0 || ws >= Ctx::SORT_WS) { ctx->err = "msm: bad result slot / workspace"; return B200_ERR_ARG; }
     Ctx::SlotInfo &si = ctx->slot_info[slot];
     si.used = false;
     if (n == 0) { si.nwin_b = 0; si.used = true; return B200_OK; }
@@ -574,15 +574,15 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const size_t PT_MAX = sizeof(G2Xyzz);   // G1 and G2 calls share the buffers: size for the larger point
 
     const int bb = slot;   // every result slot owns its bucket / partial / segment buffers
-    B200_TRY(ctx_reserve(ctx, ctx->w_hist, hist_len * 4));
-    B200_TRY(ctx_reserve(ctx, ctx->w_cursor, hist_len * 4));
-    B200_TRY(ctx_reserve(ctx, ctx->w_scan_totals, (size_t)ntiles * 4 + 16));
-    B200_TRY(ctx_reserve(ctx, ctx->w_entries, max_entries * 4 + 16));
+    B200_TRY(ctx_reserve(ctx, ctx->w_hist[ws], hist_len * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_cursor[ws], hist_len * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_scan_totals[ws], (size_t)ntiles * 4 + 16));
+    B200_TRY(ctx_reserve(ctx, ctx->w_entries[ws], max_entries * 4 + 16));
     B200_TRY(ctx_reserve(ctx, ctx->w_buckets[bb], (size_t)g.NB * PT_MAX));
     B200_TRY(ctx_reserve(ctx, ctx->w_partial[bb], max_partials * PT_MAX));
-    B200_TRY(ctx_reserve(ctx, ctx->w_hot, ((size_t)3 * g.NB + 8) * 4));
-    B200_TRY(ctx_reserve(ctx, ctx->w_plan, (size_t)(2 * SCAN_TILE + 16) * 4));
-    B200_TRY(ctx_reserve(ctx, ctx->w_tasks, max_tasks * sizeof(uint2)));
+    B200_TRY(ctx_reserve(ctx, ctx->w_hot[ws], ((size_t)3 * g.NB + 8) * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_plan[ws], (size_t)(2 * SCAN_TILE + 16) * 4));
+    B200_TRY(ctx_reserve(ctx, ctx->w_tasks[ws], max_tasks * sizeof(uint2)));
     const u32 npl1 = g.nplanes + 1;
     const size_t MSM_SLOT_PTS = 512;   // (planes + 1) x bucket sets per result slot
     if ((size_t)npl1 * g.nwin_b > MSM_SLOT_PTS) { ctx->err = "msm: too many window x plane sums"; return B200_ERR_ARG; }
@@ -590,12 +590,12 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     B200_TRY(ctx_reserve(ctx, ctx->w_win, (size_t)Ctx::MSM_SLOTS * MSM_SLOT_PTS * PT_MAX));
     B200_TRY(ctx_pinned(ctx, (size_t)Ctx::MSM_SLOTS * MSM_SLOT_PTS * PT_MAX));
 
-    u32 *d_hist = (u32 *)ctx->w_hist.p, *d_cursor = (u32 *)ctx->w_cursor.p, *d_totals = (u32 *)ctx->w_scan_totals.p;
-    u32 *d_entries = (u32 *)ctx->w_entries.p;
-    u32 *d_hot_base = (u32 *)ctx->w_hot.p, *d_hot_list = d_hot_base + g.NB, *d_warm_list = d_hot_list + g.NB;
+    u32 *d_hist = (u32 *)ctx->w_hist[ws].p, *d_cursor = (u32 *)ctx->w_cursor[ws].p, *d_totals = (u32 *)ctx->w_scan_totals[ws].p;
+    u32 *d_entries = (u32 *)ctx->w_entries[ws].p;
+    u32 *d_hot_base = (u32 *)ctx->w_hot[ws].p, *d_hot_list = d_hot_base + g.NB, *d_warm_list = d_hot_list + g.NB;
     // plan buffer: [0..4095] task-length histogram (then its scan), [4096..8191] scan cursors, [8192..] counters
-    u32 *d_lenhist = (u32 *)ctx->w_plan.p, *d_lencur = d_lenhist + SCAN_TILE, *d_plan = d_lenhist + 2 * SCAN_TILE;
-    uint2 *d_tasks = (uint2 *)ctx->w_tasks.p;
+    u32 *d_lenhist = (u32 *)ctx->w_plan[ws].p, *d_lencur = d_lenhist + SCAN_TILE, *d_plan = d_lenhist + 2 * SCAN_TILE;
+    uint2 *d_tasks = (uint2 *)ctx->w_tasks[ws].p;
     Pt *d_buckets = (Pt *)ctx->w_buckets[bb].p, *d_partial = (Pt *)ctx->w_partial[bb].p;
     Pt *d_segs = (Pt *)ctx->w_segs[bb].p;
     Pt *d_win = (Pt *)((uint8_t *)ctx->w_win.p + (size_t)slot * MSM_SLOT_PTS * PT_MAX);
@@ -619,24 +619,31 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
         const int add_existing = batch_idx > 0 ? 1 : 0;
 
         if (!reuse_sort) {
-            // the previous MSM's side-stream merge still reads the offsets / plan of the previous sort
+            cudaStream_t ss = sort_stream ? sort_stream : st;
+            // side-stream merges of earlier MSMs may still read this workspace's offsets / plan
             for (int r = 0; r < Ctx::MSM_SLOTS; r++)
-                if (ctx->sort_readers & (1u << r)) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_merge[r], 0));
-            ctx->sort_readers = 0;
-            phase_begin(ctx, PH_MSM_SORT);
-            B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_hist, 0, hist_len * 4, st));
-            B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_lenhist, 0, (size_t)(2 * SCAN_TILE + 16) * 4, st));
-            B200_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_hist, (u32 *)nullptr);
-            B200_LAUNCH(ctx, k_scan_tile, ntiles, 1024, 0, d_hist, d_totals);
-            B200_LAUNCH(ctx, k_scan_totals, 1, 1024, 0, d_totals, ntiles);
-            B200_LAUNCH(ctx, k_scan_add, ntiles, 1024, 0, d_hist, d_totals, d_cursor);
-            B200_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_cursor, d_entries);
+                if (ctx->sort_readers[ws] & (1u << r)) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(ss, ctx->ev_merge[r], 0));
+            ctx->sort_readers[ws] = 0;
+            // ... and so may the last accumulation that used it, if that is still queued on the main stream
+            if (ss != st && ctx->ws_acc_pending[ws]) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(ss, ctx->ev_ws_acc[ws], 0));
+            phase_begin(ctx, PH_MSM_SORT, ss);
+            B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_hist, 0, hist_len * 4, ss));
+            B200_CUDA_CHECK(ctx, cudaMemsetAsync(d_lenhist, 0, (size_t)(2 * SCAN_TILE + 16) * 4, ss));
+            B200_LAUNCH_ON(ctx, ss, k_msm_digits<false>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_hist, (u32 *)nullptr);
+            B200_LAUNCH_ON(ctx, ss, k_scan_tile, ntiles, 1024, 0, d_hist, d_totals);
+            B200_LAUNCH_ON(ctx, ss, k_scan_totals, 1, 1024, 0, d_totals, ntiles);
+            B200_LAUNCH_ON(ctx, ss, k_scan_add, ntiles, 1024, 0, d_hist, d_totals, d_cursor);
+            B200_LAUNCH_ON(ctx, ss, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_cursor, d_entries);
             // task plan: histogram of task lengths (descending), scan, placement
-            B200_LAUNCH(ctx, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list, d_warm_list);
-            B200_LAUNCH(ctx, k_scan_tile, 1, 1024, 0, d_lenhist, d_plan + 2);      // d_plan[2] = number of tasks
-            B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, st));
-            B200_LAUNCH(ctx, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
-            phase_end(ctx);
+            B200_LAUNCH_ON(ctx, ss, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list, d_warm_list);
+            B200_LAUNCH_ON(ctx, ss, k_scan_tile, 1, 1024, 0, d_lenhist, d_plan + 2);      // d_plan[2] = number of tasks
+            B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, ss));
+            B200_LAUNCH_ON(ctx, ss, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
+            phase_end(ctx, ss);
+            if (ss != st) {
+                B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_sort[ws], ss));
+                B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_sort[ws], 0));
+            }
         }
 
         phase_begin(ctx, g2 ? PH_MSM_ACCUM_G2 : PH_MSM_ACCUM);
@@ -652,6 +659,8 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             B200_LAUNCH(ctx, kacc, agrid, 128, smem, bs, d_entries, d_hist, d_tasks, d_plan + 2, g.CAP, d_hot_base, d_buckets, d_partial, add_existing);
         }
         phase_end(ctx);
+        B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_ws_acc[ws], st));
+        ctx->ws_acc_pending[ws] = true;
 
         // folding of split buckets: on the side stream for the last (usually only) batch so that it overlaps the
         // next MSM's sort and accumulation; earlier batches must finish before the next batch accumulates
@@ -667,7 +676,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
         phase_end(ctx, ms);
         if (last_batch) {
             B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_merge[slot], side));
-            ctx->sort_readers |= 1u << slot;
+            ctx->sort_readers[ws] |= 1u << slot;
         }
     }
 

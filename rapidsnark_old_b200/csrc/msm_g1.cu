@@ -8,15 +8,15 @@ static MsmTable<Fq> as_table_g1(const MsmTableRaw *table) {
     return t;
 }
 int msm_g1_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
-                   const MsmTableRaw *table, bool reuse_sort, bool tail) {
+                   const MsmTableRaw *table, bool reuse_sort, bool tail, int ws, cudaStream_t sort_stream) {
     MsmTable<Fq> t = as_table_g1(table);
-    return msm_enqueue_impl<Fq>(ctx, d_bases, d_scalars, scalar_size, n, slot, &t, reuse_sort, tail);
+    return msm_enqueue_impl<Fq>(ctx, d_bases, d_scalars, scalar_size, n, slot, &t, reuse_sort, tail, ws, sort_stream);
 }
 int msm_g1_collect(Ctx *ctx, int slot, G1Xyzz *out_host) { return msm_collect_impl<Fq>(ctx, slot, out_host); }
 int msm_g1_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G1Xyzz *out_host,
                const MsmTableRaw *table) {
     *out_host = G1Xyzz::zero();
-    B200_TRY(msm_g1_enqueue(ctx, d_bases, d_scalars, scalar_size, n, 0, table, false, true));
+    B200_TRY(msm_g1_enqueue(ctx, d_bases, d_scalars, scalar_size, n, 0, table, false, true, 0, nullptr));
     return msm_g1_collect(ctx, 0, out_host);
 }
 int msm_g1_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl) {

@@ -8,15 +8,15 @@ static MsmTable<Fq2> as_table_g2(const MsmTableRaw *table) {
     return t;
 }
 int msm_g2_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
-                   const MsmTableRaw *table, bool reuse_sort, bool tail) {
+                   const MsmTableRaw *table, bool reuse_sort, bool tail, int ws, cudaStream_t sort_stream) {
     MsmTable<Fq2> t = as_table_g2(table);
-    return msm_enqueue_impl<Fq2>(ctx, d_bases, d_scalars, scalar_size, n, slot, &t, reuse_sort, tail);
+    return msm_enqueue_impl<Fq2>(ctx, d_bases, d_scalars, scalar_size, n, slot, &t, reuse_sort, tail, ws, sort_stream);
 }
 int msm_g2_collect(Ctx *ctx, int slot, G2Xyzz *out_host) { return msm_collect_impl<Fq2>(ctx, slot, out_host); }
 int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, G2Xyzz *out_host,
                const MsmTableRaw *table) {
     *out_host = G2Xyzz::zero();
-    B200_TRY(msm_g2_enqueue(ctx, d_bases, d_scalars, scalar_size, n, 0, table, false, true));
+    B200_TRY(msm_g2_enqueue(ctx, d_bases, d_scalars, scalar_size, n, 0, table, false, true, 0, nullptr));
     return msm_g2_collect(ctx, 0, out_host);
 }
 int msm_g2_precompute(Ctx *ctx, const void *d_pts, u32 n, int c, void *d_tbl) {

@@ -366,8 +366,10 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom, false));
     B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom, false));
     B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom, false));
-    B200_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_h, 0));   // h scalars ready (H pipeline stream)
-    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true));
+    // the digit sort of h runs on the H-pipeline stream right behind the NTTs (own sort workspace), i.e. under the
+    // witness accumulations; only the H accumulation itself waits for it on the main stream
+    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true,
+                            1, c->hstream));
     B200_TRY(msm_g1_collect(c, 0, &pih));
     B200_TRY(msm_g2_collect(c, 1, &pib));
     B200_TRY(msm_g1_collect(c, 2, &pia));
