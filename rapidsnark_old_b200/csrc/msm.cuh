@@ -640,10 +640,8 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, ss));
             B200_LAUNCH_ON(ctx, ss, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
             phase_end(ctx, ss);
-            if (ss != st) {
-                B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_sort[ws], ss));
-                B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_sort[ws], 0));
-            }
+            B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_sort[ws], ss));   // "sorted": also lets callers chain other streams
+            if (ss != st) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_sort[ws], 0));
         }
 
         phase_begin(ctx, g2 ? PH_MSM_ACCUM_G2 : PH_MSM_ACCUM);

@@ -306,15 +306,19 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
 // witness upload, then a,b,c -> h.  With `overlap` the H pipeline runs on its own stream (c->hstream) so that
 // the witness MSMs, which do not depend on it, can start right after the upload; the caller makes the H MSM
 // wait on c->ev_h.
-static int h_on_device(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, bool overlap = false) {
+static int wtns_upload(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device) {
     phase_begin(c, PH_H2D);
     B200_CUDA_CHECK(c, cudaMemcpyAsync(zk->d_wtns, wtns, (size_t)zk->n_vars * 32,
                                         wtns_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     phase_end(c);
+    return B200_OK;
+}
+
+// `after`: event on another stream the H pipeline has to wait for (witness uploaded / witness digits sorted)
+static int h_on_device(Ctx *c, b200_zkey *zk, bool overlap = false, cudaEvent_t after = nullptr) {
     cudaStream_t main_stream = c->stream;
     if (overlap) {
-        B200_CUDA_CHECK(c, cudaEventRecord(c->ev_h, main_stream));
-        B200_CUDA_CHECK(c, cudaStreamWaitEvent(c->hstream, c->ev_h, 0));
+        if (after) B200_CUDA_CHECK(c, cudaStreamWaitEvent(c->hstream, after, 0));
         c->stream = c->hstream;           // build_abc / h_pipeline launch on c->stream
     }
     int rc = B200_OK;
@@ -338,7 +342,8 @@ int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_ou
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     phase_reset(c);
-    B200_TRY(h_on_device(c, zk, wtns_host, false));
+    B200_TRY(wtns_upload(c, zk, wtns_host, false));
+    B200_TRY(h_on_device(c, zk));
     B200_CUDA_CHECK(c, cudaMemcpyAsync(h_out_host, zk->d_a, (size_t)zk->domain_size * 32, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     phase_collect(c);
@@ -350,7 +355,8 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     phase_reset(c);
-    B200_TRY(h_on_device(c, zk, wtns_host, wtns_on_device, true));
+    B200_TRY(wtns_upload(c, zk, wtns_host, wtns_on_device));
+    B200_CUDA_CHECK(c, cudaEventRecord(c->ev_h, c->stream));   // "witness uploaded"
     uint8_t *o = (uint8_t *)out768;
     G1Xyzz pih, pia, pib1, pic;
     G2Xyzz pib;
@@ -363,6 +369,9 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
                            lenA <= (1u << 24);
     // order: the G2 MSM first (its long bucket reduction then hides behind four G1 accumulations), H last
     B200_TRY(msm_g2_enqueue(c, zk->d_B2, w + zk->rA.lo * 32, 32, lenA, 1, &zk->tB2, false, false));
+    // H pipeline on its own stream, started once the witness digits are sorted (the sort is atomics-bound and would
+    // only be slowed down by the NTT kernels; the G2 accumulation that follows absorbs them)
+    B200_TRY(h_on_device(c, zk, true, lenA ? c->ev_sort[0] : c->ev_h));
     B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom, false));
     B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom, false));
     B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom, false));
