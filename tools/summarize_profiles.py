@@ -38,9 +38,11 @@ if os.path.exists(lc):
         v = float(r[vi].replace(",", ""))
         ms = v / 1e6 if r[ui] == "ns" else v / 1e3 if r[ui] in ("us", "usecond") else v
         data.append((short(r[ki]), ms))
-    # one proof = from the last k_build_abc to the end
+    # one proof = the last `period` launches, period = distance between consecutive k_build_abc launches
+    # (the witness sort and the G2 accumulation are enqueued before the H pipeline, so a proof does not start there)
     starts = [i for i, d in enumerate(data) if d[0].startswith("k_build_abc")]
-    last = data[starts[-1]:]
+    period = starts[-1] - starts[-2] if len(starts) > 1 else len(data)
+    last = data[len(data) - period:]
     agg = collections.OrderedDict()
     for n, ms in last:
         a = agg.setdefault(n, [0, 0.0])
