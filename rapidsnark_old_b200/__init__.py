@@ -14,7 +14,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200snark.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libb200snark.so")   # B200_LIB: A/B builds of the same ABI
 
 OK, ERR_ARG, ERR_CUDA, ERR_NO_GPU, ERR_RANGE = 0, 1, 2, 3, 4
 

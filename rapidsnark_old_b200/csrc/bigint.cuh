@@ -34,6 +34,7 @@ DEVFN u32 subc_cc(u32 a, u32 b) { u32 r; asm volatile("subc.cc.u32 %0, %1, %2;" 
 DEVFN u32 subc(u32 a, u32 b) { u32 r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 DEVFN u32 mul_lo(u32 a, u32 b) { return a * b; }
 DEVFN u32 mul_hi(u32 a, u32 b) { return __umulhi(a, b); }
+DEVFN void mul_wide(u32 &lo, u32 &hi, u32 a, u32 b) { u64 p = (u64)a * b; lo = (u32)p; hi = (u32)(p >> 32); }
 DEVFN u32 mad_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 DEVFN u32 madc_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 DEVFN u32 mad_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -51,6 +52,7 @@ inline u32 subc_cc(u32 a, u32 b) { u64 t = (u64)a - b - g_cf; g_cf = (u32)((t >>
 inline u32 subc(u32 a, u32 b) { return a - b - g_cf; }
 inline u32 mul_lo(u32 a, u32 b) { return a * b; }
 inline u32 mul_hi(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
+inline void mul_wide(u32 &lo, u32 &hi, u32 a, u32 b) { u64 p = (u64)a * b; lo = (u32)p; hi = (u32)(p >> 32); }
 inline u32 mad_lo_cc(u32 a, u32 b, u32 c) { return add_cc(mul_lo(a, b), c); }
 inline u32 madc_lo_cc(u32 a, u32 b, u32 c) { return addc_cc(mul_lo(a, b), c); }
 inline u32 mad_hi_cc(u32 a, u32 b, u32 c) { return add_cc(mul_hi(a, b), c); }

@@ -94,6 +94,8 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     if (!h || !name) return B200_ERR_ARG;
     if (!strcmp(name, "msm_window")) h->c.force_c = value;
     else if (!strcmp(name, "acc_smem")) h->c.opt_acc_smem = value;
+    else if (!strcmp(name, "g2_minb")) h->c.opt_g2_minb = value;
+    else if (!strcmp(name, "g1_minb")) h->c.opt_g1_minb = value;
     else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;
     else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;
     else if (!strcmp(name, "target_tasks_log2")) h->c.opt_target_tasks_log2 = value;

@@ -46,6 +46,8 @@ struct Ctx {
     int sm_count = 148;
     int force_c = 0;
     int opt_acc_smem = -1;   // -1 auto, 0 registers, 1 shared memory (experiments)
+    int opt_g1_minb = 0;     // 0 auto; 3 / 4 for the G1 accumulation (168 / 128 registers)
+    int opt_g2_minb = 0;     // 0 auto; 2 / 3: resident CTAs per SM the G2 accumulation is compiled for (255 / 168 registers)
     int opt_precomp = -1;    // -1 auto (on), 0 off; window bits of resident tables in opt_precomp_c
     int opt_precomp_c = 0;
     float phase_ms[PH_COUNT] = {0};

@@ -50,7 +50,7 @@ HD_COLD Xyzz<F> ec_dbl_affine(const Affine<F> &p) {
     F xx = csqr(p.x);
     F m = fadd(fdbl(xx), xx);
     r.x = fsub(csqr(m), fdbl(s));
-    r.y = fsub(cmul(m, fsub(s, r.x)), cmul(w, p.y));
+    r.y = cmul_sub_mul(m, fsub(s, r.x), w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -68,7 +68,7 @@ HD_COLD Xyzz<F> ec_dbl(const Xyzz<F> &p) {
     F xx = csqr(p.x);
     F m = fadd(fdbl(xx), xx);
     r.x = fsub(csqr(m), fdbl(s));
-    r.y = fsub(cmul(m, fsub(s, r.x)), cmul(w, p.y));
+    r.y = cmul_sub_mul(m, fsub(s, r.x), w, p.y);
     r.zz = cmul(v, p.zz);
     r.zzz = cmul(w, p.zzz);
     return r;
@@ -103,21 +103,21 @@ HD void ec_madd_acc(Acc &acc, const Affine<F> &q) {
     }
     F zzz = acc.ld_zzz();
     F x1 = acc.ld_x(), y1 = acc.ld_y();
-    F p = fsub(fmul(q.x, zz), x1);
-    F r = fsub(fmul(q.y, zzz), y1);
+    F p = fsub(hmul(q.x, zz), x1);
+    F r = fsub(hmul(q.y, zzz), y1);
     if (p.is_zero()) {
         if (r.is_zero()) acc.st_all(ec_dbl_affine(q));   // same point
         else acc.st_all(Xyzz<F>::zero());                 // opposite points
         return;
     }
-    F pp = fsqr(p);
-    F ppp = fmul(p, pp);
-    acc.st_zz(fmul(zz, pp));
-    acc.st_zzz(fmul(zzz, ppp));
-    F qq = fmul(x1, pp);
-    F x3 = fsub(fsub(fsqr(r), ppp), fdbl(qq));
+    F pp = hsqr(p);
+    F ppp = hmul(p, pp);
+    acc.st_zz(hmul(zz, pp));
+    acc.st_zzz(hmul(zzz, ppp));
+    F qq = hmul(x1, pp);
+    F x3 = fsub(fsub(hsqr(r), ppp), fdbl(qq));
     acc.st_x(x3);
-    acc.st_y(fsub(fmul(r, fsub(qq, x3)), fmul(y1, ppp)));
+    acc.st_y(hmul_sub_mul(r, fsub(qq, x3), y1, ppp));
 }
 
 template <class F>
@@ -148,7 +148,7 @@ HD_COLD void ec_add(Xyzz<F> &acc, const Xyzz<F> &q) {
     F ppp = cmul(p, pp);
     F qq = cmul(u1, pp);
     F x3 = fsub(fsub(csqr(r), ppp), fdbl(qq));
-    F y3 = fsub(cmul(r, fsub(qq, x3)), cmul(s1, ppp));
+    F y3 = cmul_sub_mul(r, fsub(qq, x3), s1, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = cmul(cmul(acc.zz, q.zz), pp);

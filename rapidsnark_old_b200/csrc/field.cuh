@@ -14,6 +14,19 @@
 #pragma once
 #include "bigint.cuh"
 
+// Build-time variants (A/B measured on B200 at 2^20):
+//   B200_KARATSUBA  0: the word-serial interleaved product (fp_mul_serial, 64 + 64 wide multiplies)      [default]
+//                   1: 512-bit products through one Karatsuba level (48 wide multiplies) + separate reduction:
+//                      12 % fewer multiplier-pipe cycles but 30 % more instructions and longer carry chains -
+//                      measured 14 % SLOWER per proof (24.3 ms vs 21.4 ms), kept only as an experiment
+//   B200_LAZY_PAIR  1: a*b - c*d shares one Montgomery reduction (Y3 of the mixed addition): -6 % per proof
+#ifndef B200_KARATSUBA
+#define B200_KARATSUBA 0
+#endif
+#ifndef B200_LAZY_PAIR
+#define B200_LAZY_PAIR 1
+#endif
+
 namespace b200 {
 
 struct FqParams {
@@ -166,10 +179,7 @@ namespace detail {
 // acc[j], acc[j+1] = a[j] * bi for j = 0,2,4,6 (four independent 32x32->64 products)
 HD void mul_pairs(u32 *acc, const u32 *a, u32 bi) {
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-        acc[j] = mul_lo(a[j], bi);
-        acc[j + 1] = mul_hi(a[j], bi);
-    }
+    for (int j = 0; j < 8; j += 2) mul_wide(acc[j], acc[j + 1], a[j], bi);
 }
 
 // acc += a_{0,2,4,6} * bi as one carry chain; carry out of acc[7] is left in the flag
@@ -223,7 +233,10 @@ HD void mont_round(u32 *lo, u32 *pend, const u32 *a, u32 bi, bool first) {
 
 // Montgomery product a*b*2^-256 mod p, fully reduced.
 template <class P>
-HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
+HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b);
+
+template <class P>
+HD Fp<P> fp_mul_serial(const Fp<P> &a, const Fp<P> &b) {
     u32 even[8], odd[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
@@ -242,15 +255,22 @@ HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
 // ---- separated product / reduction (used by the lazily reduced Fq2 product in fq2.cuh) ----------------------
 namespace detail {
 
-// t[0..15] = a[0..7] * b[0..7], plain 512-bit product.  Same even/odd accumulator idea as mont_round: E holds the
-// 64-bit partial products whose low word sits at an even position, O those at odd positions (O[k] = position
-// k+1), so every product is one IMAD.WIDE with an aligned addend; the two are added once at the end.
-HD void mul8x8(u32 *t, const u32 *a, const u32 *b) {
-    u32 E[16], O[16];
+// t[0..2N-1] = a[0..N-1] * b[0..N-1], plain product (N even).  Same even/odd accumulator idea as mont_round: E holds
+// the 64-bit partial products whose low word sits at an even position, O those at odd positions (O[k] = position
+// k+1), so every product is one IMAD.WIDE with an aligned addend; the two are added once at the end.  Row 0 has
+// nothing to accumulate onto and is written as plain 64-bit products.
+template <int N>
+HD void mul_nxn(u32 *t, const u32 *a, const u32 *b) {
+    u32 E[2 * N], O[2 * N];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { E[k] = 0; O[k] = 0; }
+    for (int j = 0; j < N; j += 2) {
+        mul_wide(E[j], E[j + 1], a[j], b[0]);
+        mul_wide(O[j], O[j + 1], a[j + 1], b[0]);
+    }
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int k = N; k < 2 * N; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 1; i < N; i++) {
         const u32 bi = b[i];
         // even limbs of a: first pair at position i; odd limbs: first pair at position i + 1
         u32 *Xe = (i & 1) ? O : E;
@@ -260,25 +280,108 @@ HD void mul8x8(u32 *t, const u32 *a, const u32 *b) {
         Xe[se] = mad_lo_cc(a[0], bi, Xe[se]);
         Xe[se + 1] = madc_hi_cc(a[0], bi, Xe[se + 1]);
 #pragma unroll
-        for (int j = 2; j < 8; j += 2) {
+        for (int j = 2; j < N; j += 2) {
             Xe[se + j] = madc_lo_cc(a[j], bi, Xe[se + j]);
             Xe[se + j + 1] = madc_hi_cc(a[j], bi, Xe[se + j + 1]);
         }
-        if (se + 8 < 16) Xe[se + 8] = addc(Xe[se + 8], 0);
+        if (se + N < 2 * N) Xe[se + N] = addc(Xe[se + N], 0);
         Xo[so] = mad_lo_cc(a[1], bi, Xo[so]);
         Xo[so + 1] = madc_hi_cc(a[1], bi, Xo[so + 1]);
 #pragma unroll
-        for (int j = 2; j < 8; j += 2) {
+        for (int j = 2; j < N; j += 2) {
             Xo[so + j] = madc_lo_cc(a[j + 1], bi, Xo[so + j]);
             Xo[so + j + 1] = madc_hi_cc(a[j + 1], bi, Xo[so + j + 1]);
         }
-        if (so + 8 < 16) Xo[so + 8] = addc(Xo[so + 8], 0);
+        if (so + N < 2 * N) Xo[so + N] = addc(Xo[so + N], 0);
     }
     t[0] = E[0];
     t[1] = add_cc(E[1], O[0]);
 #pragma unroll
-    for (int k = 2; k < 15; k++) t[k] = addc_cc(E[k], O[k - 1]);
-    t[15] = addc(E[15], O[14]);
+    for (int k = 2; k < 2 * N - 1; k++) t[k] = addc_cc(E[k], O[k - 1]);
+    t[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
+}
+
+#if B200_KARATSUBA
+// t[0..15] = a[0..7] * b[0..7] for any 256-bit a, b: one level of Karatsuba over the 128-bit halves, 3 x 16 wide
+// multiplies instead of 64 (the multiplier pipe is what bounds every kernel here; the extra additions run on the
+// ALU pipe beside it).   a b = z0 + (zm - z0 - z2) 2^128 + z2 2^256,  zm = (a0 + a1)(b0 + b1) as a 9-limb value
+HD void mul8x8(u32 *t, const u32 *a, const u32 *b) {
+    u32 zm[9], sa[4], sb[4];
+    mul_nxn<4>(t, a, b);
+    mul_nxn<4>(t + 8, a + 4, b + 4);
+    sa[0] = add_cc(a[0], a[4]);
+    sa[1] = addc_cc(a[1], a[5]);
+    sa[2] = addc_cc(a[2], a[6]);
+    sa[3] = addc_cc(a[3], a[7]);
+    const u32 ca = addc(0, 0);
+    sb[0] = add_cc(b[0], b[4]);
+    sb[1] = addc_cc(b[1], b[5]);
+    sb[2] = addc_cc(b[2], b[6]);
+    sb[3] = addc_cc(b[3], b[7]);
+    const u32 cb = addc(0, 0);
+    mul_nxn<4>(zm, sa, sb);
+    const u32 ma = 0u - ca, mb = 0u - cb;          // the carries of the two sums: (sa + ca 2^128)(sb + cb 2^128)
+    zm[4] = add_cc(zm[4], sb[0] & ma);
+    zm[5] = addc_cc(zm[5], sb[1] & ma);
+    zm[6] = addc_cc(zm[6], sb[2] & ma);
+    zm[7] = addc_cc(zm[7], sb[3] & ma);
+    zm[8] = addc(ca & cb, 0);
+    zm[4] = add_cc(zm[4], sa[0] & mb);
+    zm[5] = addc_cc(zm[5], sa[1] & mb);
+    zm[6] = addc_cc(zm[6], sa[2] & mb);
+    zm[7] = addc_cc(zm[7], sa[3] & mb);
+    zm[8] = addc(zm[8], 0);
+    zm[0] = sub_cc(zm[0], t[0]);                     // zm -= z0; zm -= z2: a0 b1 + a1 b0 >= 0
+#pragma unroll
+    for (int i = 1; i < 8; i++) zm[i] = subc_cc(zm[i], t[i]);
+    zm[8] = subc(zm[8], 0);
+    zm[0] = sub_cc(zm[0], t[8]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) zm[i] = subc_cc(zm[i], t[8 + i]);
+    zm[8] = subc(zm[8], 0);
+    t[4] = add_cc(t[4], zm[0]);
+#pragma unroll
+    for (int i = 1; i < 9; i++) t[4 + i] = addc_cc(t[4 + i], zm[i]);
+    t[13] = addc_cc(t[13], 0);
+    t[14] = addc_cc(t[14], 0);
+    t[15] = addc(t[15], 0);
+}
+
+// t = a^2 through the same 4 x 4 blocks: a0^2 + 2 a0 a1 2^128 + a1^2 2^256
+HD void sqr8(u32 *t, const u32 *a) {
+    u32 zm[8];
+    mul_nxn<4>(t, a, a);
+    mul_nxn<4>(t + 8, a + 4, a + 4);
+    mul_nxn<4>(zm, a, a + 4);
+    const u32 top = zm[7] >> 31;
+#pragma unroll
+    for (int i = 7; i > 0; i--) zm[i] = (zm[i] << 1) | (zm[i - 1] >> 31);
+    zm[0] <<= 1;
+    t[4] = add_cc(t[4], zm[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[4 + i] = addc_cc(t[4 + i], zm[i]);
+    t[12] = addc_cc(t[12], top);
+    t[13] = addc_cc(t[13], 0);
+    t[14] = addc_cc(t[14], 0);
+    t[15] = addc(t[15], 0);
+}
+#else
+HD void mul8x8(u32 *t, const u32 *a, const u32 *b) { mul_nxn<8>(t, a, b); }
+HD void sqr8(u32 *t, const u32 *a) { mul_nxn<8>(t, a, a); }
+#endif
+
+// t -= s over 16 limbs; when the difference is negative p * 2^256 is added back, so for |t - s| < p * 2^256 the
+// result is a valid mont_reduce16 input congruent to t - s
+template <class P>
+HD void sub16_mod(u32 *t, const u32 *s) {
+    t[0] = sub_cc(t[0], s[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) t[i] = subc_cc(t[i], s[i]);
+    const u32 borrow = subc(0, 0);
+    t[8] = add_cc(t[8], borrow & P::mod(0));
+#pragma unroll
+    for (int i = 1; i < 7; i++) t[8 + i] = addc_cc(t[8 + i], borrow & P::mod(i));
+    t[15] = addc(t[15], borrow & P::mod(7));
 }
 
 // Montgomery reduction of a 16-limb value t < p * 2^256: r = t * 2^-256 mod p, r < 2p before the final
@@ -321,8 +424,49 @@ HD void mont_reduce16(u32 *r, const u32 *t) {
 }  // namespace detail
 
 template <class P>
+HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
+#if B200_KARATSUBA
+    u32 t[16];
+    detail::mul8x8(t, a.v, b.v);
+    Fp<P> r;
+    detail::mont_reduce16<P>(r.v, t);
+    fp_reduce_once(r);
+    return r;
+#else
+    return fp_mul_serial(a, b);
+#endif
+}
+
+template <class P>
 HD Fp<P> fp_sqr(const Fp<P> &a) {
+#if B200_KARATSUBA
+    u32 t[16];
+    detail::sqr8(t, a.v);
+    Fp<P> r;
+    detail::mont_reduce16<P>(r.v, t);
+    fp_reduce_once(r);
+    return r;
+#else
     return fp_mul(a, a);
+#endif
+}
+
+// a*b - c*d with ONE Montgomery reduction: the two 512-bit products are subtracted first (|a b - c d| < p^2 <
+// p * 2^256).  Same canonical value as fp_sub(fp_mul(a, b), fp_mul(c, d)).
+template <class P>
+HD Fp<P> fp_mul_sub_mul(const Fp<P> &a, const Fp<P> &b, const Fp<P> &c, const Fp<P> &d) {
+#if B200_LAZY_PAIR
+    u32 t[16], s[16];
+    detail::mul8x8(t, a.v, b.v);
+    detail::mul8x8(s, c.v, d.v);
+    detail::sub16_mod<P>(t, s);
+    Fp<P> r;
+    detail::mont_reduce16<P>(r.v, t);
+    fp_reduce_once(r);
+    return r;
+#else
+    return fp_sub(fp_mul(a, b), fp_mul(c, d));
+#endif
 }
 
 template <class P>

@@ -94,6 +94,70 @@ HD Fq2T<Fq> fmul(const Fq2T<Fq> &x, const Fq2T<Fq> &y) {
     return r;
 }
 
+// x*y - z*w (the Y3 of the mixed addition) with one reduction per component instead of two
+HD Fq fmul_sub_mul(const Fq &x, const Fq &y, const Fq &z, const Fq &w) { return fp_mul_sub_mul(x, y, z, w); }
+HD Fr fmul_sub_mul(const Fr &x, const Fr &y, const Fr &z, const Fr &w) { return fp_mul_sub_mul(x, y, z, w); }
+template <class B>
+HD Fq2T<B> fmul_sub_mul(const Fq2T<B> &x, const Fq2T<B> &y, const Fq2T<B> &z, const Fq2T<B> &w) {
+    return fsub(fmul(x, y), fmul(z, w));
+}
+#if B200_LAZY_PAIR
+namespace detail {
+// c0 = a0 b0 - a1 b1, c1 = a0 b1 + a1 b0 as unreduced 512-bit values: c0 may be negative and is returned as
+// c0 mod 2^512 with its sign in the return value (all-ones = negative); 0 <= c1 < 2 p^2
+HD u32 fq2_mul_wide(u32 *c0, u32 *c1, const Fq2T<Fq> &x, const Fq2T<Fq> &y) {
+    u32 t1[16], sa[8], sb[8];
+    mul8x8(c0, x.a.v, y.a.v);
+    mul8x8(t1, x.b.v, y.b.v);
+    sa[0] = add_cc(x.a.v[0], x.b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) sa[i] = addc_cc(x.a.v[i], x.b.v[i]);
+    sa[7] = addc(x.a.v[7], x.b.v[7]);
+    sb[0] = add_cc(y.a.v[0], y.b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) sb[i] = addc_cc(y.a.v[i], y.b.v[i]);
+    sb[7] = addc(y.a.v[7], y.b.v[7]);
+    mul8x8(c1, sa, sb);
+    c1[0] = sub_cc(c1[0], c0[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) c1[i] = subc_cc(c1[i], c0[i]);
+    c1[15] = subc(c1[15], c0[15]);
+    c1[0] = sub_cc(c1[0], t1[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) c1[i] = subc_cc(c1[i], t1[i]);
+    c1[15] = subc(c1[15], t1[15]);
+    c0[0] = sub_cc(c0[0], t1[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) c0[i] = subc_cc(c0[i], t1[i]);
+    return subc(0, 0);
+}
+}  // namespace detail
+
+// |c0|, |c1| of the difference stay below 2 p^2 < p * 2^255, so one conditional + p * 2^256 makes each a valid
+// Montgomery-reduction input: 6 products and 2 reductions instead of 6 and 4
+HD Fq2T<Fq> fmul_sub_mul(const Fq2T<Fq> &x, const Fq2T<Fq> &y, const Fq2T<Fq> &z, const Fq2T<Fq> &w) {
+    u32 c0[16], c1[16], d0[16], d1[16];
+    u32 neg0 = detail::fq2_mul_wide(c0, c1, x, y);
+    u32 negd = detail::fq2_mul_wide(d0, d1, z, w);
+    // c0 - d0 as a signed 512 + 1 bit value: sign word = neg0 - negd - borrow
+    c0[0] = sub_cc(c0[0], d0[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) c0[i] = subc_cc(c0[i], d0[i]);
+    u32 s0 = subc(neg0, negd);                       // 0 = non-negative, all-ones = negative (|value| < 2^511)
+    c0[8] = add_cc(c0[8], s0 & FqParams::mod(0));
+#pragma unroll
+    for (int i = 1; i < 7; i++) c0[8 + i] = addc_cc(c0[8 + i], s0 & FqParams::mod(i));
+    c0[15] = addc(c0[15], s0 & FqParams::mod(7));
+    detail::sub16_mod<FqParams>(c1, d1);
+    Fq2T<Fq> r;
+    detail::mont_reduce16<FqParams>(r.a.v, c0);
+    fp_reduce_once(r.a);
+    detail::mont_reduce16<FqParams>(r.b.v, c1);
+    fp_reduce_once(r.b);
+    return r;
+}
+#endif
+
 // complex squaring, 2 base-field products (f2field.cpp:114-126)
 template <class B>
 HD Fq2T<B> fsqr(const Fq2T<B> &x) {
@@ -121,5 +185,22 @@ template <class F> HD F cmul(const F &x, const F &y) { return fmul(x, y); }
 template <class F> HD F csqr(const F &x) { return fsqr(x); }
 template <class B> HD_COLD Fq2T<B> cmul(const Fq2T<B> &x, const Fq2T<B> &y) { return fmul(x, y); }
 template <class B> HD_COLD Fq2T<B> csqr(const Fq2T<B> &x) { return fsqr(x); }
+template <class F> HD F cmul_sub_mul(const F &x, const F &y, const F &z, const F &w) { return fmul_sub_mul(x, y, z, w); }
+template <class B> HD_COLD Fq2T<B> cmul_sub_mul(const Fq2T<B> &x, const Fq2T<B> &y, const Fq2T<B> &z, const Fq2T<B> &w) { return fmul_sub_mul(x, y, z, w); }
+
+// Products of the HOT mixed addition.  B200_G2_HOT_CALLS = 1 routes the Fq2 ones through the out-of-line copies
+// too (operands through the local-memory stack): ~3x less code in the G2 accumulation loop, fewer live registers.
+#ifndef B200_G2_HOT_CALLS
+#define B200_G2_HOT_CALLS 0
+#endif
+#if B200_G2_HOT_CALLS
+template <class F> HD F hmul(const F &x, const F &y) { return cmul(x, y); }
+template <class F> HD F hsqr(const F &x) { return csqr(x); }
+template <class F> HD F hmul_sub_mul(const F &x, const F &y, const F &z, const F &w) { return cmul_sub_mul(x, y, z, w); }
+#else
+template <class F> HD F hmul(const F &x, const F &y) { return fmul(x, y); }
+template <class F> HD F hsqr(const F &x) { return fsqr(x); }
+template <class F> HD F hmul_sub_mul(const F &x, const F &y, const F &z, const F &w) { return fmul_sub_mul(x, y, z, w); }
+#endif
 
 }  // namespace b200

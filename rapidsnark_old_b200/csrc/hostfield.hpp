@@ -130,6 +130,8 @@ inline HFp<P> fmul(const HFp<P> &a, const HFp<P> &b) {
 
 template <class P>
 inline HFp<P> fsqr(const HFp<P> &a) { return fmul(a, a); }
+template <class P>
+inline HFp<P> fmul_sub_mul(const HFp<P> &a, const HFp<P> &b, const HFp<P> &c, const HFp<P> &d) { return fsub(fmul(a, b), fmul(c, d)); }
 
 template <class P>
 inline HFp<P> finv(const HFp<P> &a) {   // a^(p-2)

@@ -604,6 +604,10 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const bool g2 = sizeof(F) != 32;
     const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
     const size_t acc_smem_bytes = 128 * sizeof(Pt);
+    static const int env_g2_minb = getenv("B200_G2_MINB") ? atoi(getenv("B200_G2_MINB")) : 0;   // experiments
+    static const int env_g1_minb = getenv("B200_G1_MINB") ? atoi(getenv("B200_G1_MINB")) : 0;
+    const int g1_minb = ctx->opt_g1_minb ? ctx->opt_g1_minb : env_g1_minb ? env_g1_minb : 3;
+    const int g2_minb = ctx->opt_g2_minb ? ctx->opt_g2_minb : env_g2_minb ? env_g2_minb : (B200_G2_HOT_CALLS ? 3 : 2);
 
     // this slot's buffers may still be read by the side-stream reduction of its previous MSM
     if (ctx->slot_busy[slot]) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_done[slot], 0));
@@ -653,7 +657,8 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             void (*kacc)(const Affine<F> *, const u32 *, const u32 *, const uint2 *, const u32 *, u32, const u32 *, Pt *, Pt *, int);
             size_t smem = 0;
             if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
-            else { kacc = g2 ? k_msm_accumulate<F, false, 2> : k_msm_accumulate<F, false, 3>; }
+            else if (g2) { kacc = g2_minb == 3 ? k_msm_accumulate<F, false, 3> : k_msm_accumulate<F, false, 2>; }
+            else { kacc = g1_minb == 4 ? k_msm_accumulate<F, false, 4> : k_msm_accumulate<F, false, 3>; }
             B200_LAUNCH(ctx, kacc, agrid, 128, smem, bs, d_entries, d_hist, d_tasks, d_plan + 2, g.CAP, d_hot_base, d_buckets, d_partial, add_existing);
         }
         phase_end(ctx);

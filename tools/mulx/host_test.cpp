@@ -1,0 +1,58 @@
+// scratch check: new field products vs the word-serial one, on the host build of field.cuh
+#include "../../rapidsnark_old_b200/csrc/curve.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+using namespace b200;
+template <class F> static F rnd(std::mt19937_64 &g, int mode) {
+    F r;
+    for (int i = 0; i < 8; i++) r.v[i] = (u32)g();
+    if (mode == 1) for (int i = 0; i < 8; i++) r.v[i] = 0xffffffffu;
+    if (mode == 2) for (int i = 0; i < 8; i++) r.v[i] = (g() & 1) ? 0xffffffffu : 0;
+    if (mode == 3) for (int i = 0; i < 8; i++) r.v[i] = (g() & 3) ? (u32)g() : 0xffffffffu;
+    r.v[7] &= 0x3fffffffu;
+    F m = F::modulus();
+    bool ge = true;
+    for (int i = 7; i >= 0; i--) { if (r.v[i] != m.v[i]) { ge = r.v[i] > m.v[i]; break; } }
+    if (ge) r = fp_sub(r, m);
+    if (mode == 4) { r = m; r.v[0] -= 1 + (u32)(g() & 3); }
+    if (mode == 5) { r = F::zero(); r.v[0] = (u32)(g() & 3); }
+    return r;
+}
+template <class F> int run(const char *name, long iters) {
+    std::mt19937_64 g(12345);
+    long bad = 0;
+    for (long it = 0; it < iters; it++) {
+        int ma = it < 1000 ? (it % 6) : (g() % 12 < 6 ? 0 : g() % 6), mb = it < 1000 ? ((it / 6) % 6) : (g() % 12 < 6 ? 0 : g() % 6);
+        F a = rnd<F>(g, ma), b = rnd<F>(g, mb), c = rnd<F>(g, g() % 6), d = rnd<F>(g, g() % 6);
+        if (fp_mul_serial(a, b) != fp_mul(a, b)) bad++;
+        if (fp_mul_serial(a, a) != fp_sqr(a)) bad++;
+        if (fp_sub(fp_mul_serial(a, b), fp_mul_serial(c, d)) != fp_mul_sub_mul(a, b, c, d)) bad++;
+    }
+    printf("%s: bad=%ld\n", name, bad);
+    return bad != 0;
+}
+static Fq2 fq2_mul_ref(const Fq2 &x, const Fq2 &y) {
+    Fq aa = fp_mul_serial(x.a, y.a), bb = fp_mul_serial(x.b, y.b);
+    Fq2 r; r.a = fp_sub(aa, bb); r.b = fp_add(fp_mul_serial(x.a, y.b), fp_mul_serial(x.b, y.a)); return r;
+}
+int run2(long iters) {
+    std::mt19937_64 g(777);
+    long bad = 0;
+    for (long it = 0; it < iters; it++) {
+        Fq2 x, y, z, w;
+        x.a = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6); x.b = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6);
+        y.a = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6); y.b = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6);
+        z.a = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6); z.b = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6);
+        w.a = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6); w.b = rnd<Fq>(g, g() % 12 < 6 ? 0 : g() % 6);
+        if (it % 5 == 0) { z = x; w = y; }
+        if (it % 7 == 0) { z = y; }
+        Fq2 m = fq2_mul_ref(x, y);
+        if (fmul(x, y) != m) bad++;
+        if (fsqr(x) != fq2_mul_ref(x, x)) bad++;
+        if (fmul_sub_mul(x, y, z, w) != fsub(m, fq2_mul_ref(z, w))) bad++;
+    }
+    printf("Fq2: bad=%ld\n", bad);
+    return bad != 0;
+}
+int main() { return run<Fq>("Fq", 1000000) | run<Fr>("Fr", 1000000) | run2(1000000); }
