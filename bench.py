@@ -190,8 +190,12 @@ def run_own(args):
     log_n = args.log_n
     s = build_inputs(log_n, 2, *gpu_point_makers(ctx))
     p, vk = s.points, s.vk
+    emu = args.emulate_shards if world == 1 else 0      # tuning aid: this GPU plays rank 0 of `emu` (no collective,
+    for kv in args.opt:                                  # result unchecked); never used for a reported line
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"],
-                         p["H"], rank, world)
+                         p["H"], 0 if emu else rank, emu if emu else world)
     wt_bytes = s.wtns_bytes()
     # witness: pinned host copy (e2e) and device copy (value)
     wt_host = torch.empty(len(wt_bytes), dtype=torch.uint8).pin_memory()
@@ -206,10 +210,17 @@ def run_own(args):
         # N > 1: the one collective of the path - all_gather of the 768-byte partial records (NCCL), fold, finalize
         return bdist.finish_proof(part, vk, r32, s32, device=torch.device("cuda", local))
 
+    dev = torch.device("cuda", local)
+    spread_h = world > 1 and not args.replicate_h    # N > 1: a, b, c transform chains on different ranks + NCCL broadcasts
+
     def step_resident():
+        if spread_h:
+            return finish(bdist.prove_msms_distributed(zk, wt_dev.data_ptr(), True, s.n, dev))
         return finish(zk.prove_msms_dev(wt_dev.data_ptr()))
 
     def step_e2e():
+        if spread_h:
+            return finish(bdist.prove_msms_distributed(zk, wt_host.data_ptr(), False, s.n, dev))
         return finish(zk.prove_msms(wt_host.data_ptr()))
 
     def barrier():
@@ -219,7 +230,8 @@ def run_own(args):
 
     # correctness gate before timing: every result is checked against the known discrete logs
     msms, proof = step_e2e()
-    check_known_dlogs(b200, s, msms, proof, r32, s32)
+    if not emu:
+        check_known_dlogs(b200, s, msms, proof, r32, s32)
 
     def timed(fn, steps, warm):
         for _ in range(warm):
@@ -266,13 +278,18 @@ def run_own(args):
             "vs_baseline": None, "dtype": "u256-mont", "data": "synthetic",
             "config": {"workload": "groth16 prove, BN254, 2^%d constraints, synthetic chain circuit" % log_n,
                        "n_vars": s.n_vars, "n_public": s.n_public, "n_coefs": s.n_coefs,
-                       "parallelism": "point-range shards x%d, 1 NCCL all_gather of 768 B partials" % world,
+                       "parallelism": ("point-range shards x%d, 1 NCCL all_gather of 768 B partials" % world) +
+                                      (", H transform chains a/b/c on ranks %s + 3 NCCL broadcasts of %d MB" %
+                                       (bdist.poly_owners(world), s.n * 32 >> 20) if spread_h else ""),
                        "l2": "inputs larger than L2 (0.5 GB of tables and coefficients per proof)"},
             "e2e": {"value": round(ms_e2e, 4), "unit": UNIT, "h2d_bytes_per_step": len(wt_bytes), "d2h_bytes_per_step": 768},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "phases_ms": {k: round(v, 4) for k, v in ph_res.items()},
             "phases_ms_e2e": {k: round(v, 4) for k, v in ph_e2e.items()}}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if emu:
+        line["config"]["emulated_shards"] = emu
+        line["metric"] += "_EMULATED_RANK0_OF_%d" % emu
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not emu:
         line["cpu_baseline"] = cpu_baseline(s)
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -353,6 +370,9 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicate-h", action="store_true", help="N > 1: every rank runs the whole H pipeline (A/B)")
+    ap.add_argument("--emulate-shards", type=int, default=0, help="tuning only: time rank 0 of K shards on one GPU")
+    ap.add_argument("--opt", nargs="*", default=[], help="tuning only: library options name=value (b200_set_option)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3

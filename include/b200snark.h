@@ -65,7 +65,8 @@ int b200_msm_g2_dev(b200_ctx *ctx, const void *d_bases_affine, const void *d_sca
 /* window size override for experiments (0 = automatic) */
 void b200_set_msm_window(b200_ctx *ctx, int c_bits);
 /* tuning knobs for experiments: "msm_window", "acc_smem" (-1 auto / 0 registers / 1 shared memory),
- * "precomp" (-1 auto / 0 off / 1 on: per-window precomputed tables for resident zkeys), "precomp_c" */
+ * "precomp" (-1 auto / 0 off / 1 on: per-window precomputed tables for resident zkeys), "precomp_c",
+ * "h_streams" (1 / 3: a, b, c transform chains on one or three streams), "g1_minb", "g2_minb" */
 int b200_set_option(b200_ctx *ctx, const char *name, int value);
 
 /* ---- NTT: replaces FFT<Fr>::fft / ifft (fft.hpp:24-25), natural order in and out ------------------ */
@@ -96,6 +97,19 @@ int b200_h_scalars(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *h_
 int b200_prove_msms(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *out768);
 /* same with the witness already in device memory (bench: inputs resident in HBM) */
 int b200_prove_msms_dev(b200_ctx *ctx, b200_zkey *zk, const void *d_wtns, void *out768);
+
+/* Two-stage form of b200_prove_msms for zkeys sharded over several GPUs (one ctx per GPU, one process per GPU).
+ * The H pipeline of groth16.cpp:101-163 is three independent transform chains (a, b, c) up to the final combine;
+ * b200_prove_begin runs only the chains in poly_mask (bit 0 = a, 1 = b, 2 = c) besides uploading the witness and
+ * enqueueing this shard's four witness MSMs, and returns WITHOUT synchronising: d_abc3[0..2] = device pointers of the
+ * domain_size x 32-byte a, b, c buffers (coset evaluations, Montgomery), *h_stream = the cudaStream_t they are
+ * produced on.  The caller exchanges the buffers so that every rank holds all three (e.g. one NCCL broadcast per
+ * polynomial from the rank that owns it, enqueued on / ordered after h_stream), then calls b200_prove_finish:
+ * combine -> h, this shard's H MSM, collection of the five partial results (out768 as b200_prove_msms).
+ * poly_mask = 7 and no exchange is exactly b200_prove_msms. */
+int b200_prove_begin(b200_ctx *ctx, b200_zkey *zk, const void *wtns, int wtns_on_device, uint32_t poly_mask,
+                     void **d_abc3, void **h_stream);
+int b200_prove_finish(b200_ctx *ctx, b200_zkey *zk, void *out768);
 
 /* ---- synthetic tables: k_i * G for known k_i (fixed-base, device side), affine Montgomery out ------ */
 int b200_fixed_base_g1(b200_ctx *ctx, const void *base_affine64, const void *scalars32, uint64_t n, void *out_affine);

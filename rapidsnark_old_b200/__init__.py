@@ -25,6 +25,7 @@ EXPORTS = [
     "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window", "b200_set_option",
     "b200_ntt_fr", "b200_ntt_fr_dev",
     "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
+    "b200_prove_begin", "b200_prove_finish",
     "b200_groth16_finalize", "b200_fq_to_decimal",
     "b200_fixed_base_g1", "b200_fixed_base_g2",
     "b200_host_fq_mul", "b200_host_fq_add", "b200_host_fq_sub", "b200_host_fq_neg", "b200_host_fq_inv",
@@ -78,6 +79,8 @@ def lib():
         L.b200_h_scalars.argtypes = [_vp, _vp, _vp, _vp]
         L.b200_prove_msms.argtypes = [_vp, _vp, _vp, _vp]
         L.b200_prove_msms_dev.argtypes = [_vp, _vp, _vp, _vp]
+        L.b200_prove_begin.argtypes = [_vp, _vp, _vp, _int, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]
+        L.b200_prove_finish.argtypes = [_vp, _vp, _vp]
         L.b200_stream.restype = _vp
         L.b200_stream.argtypes = [_vp]
         L.b200_groth16_finalize.argtypes = [_vp] * 9
@@ -167,6 +170,21 @@ class ZKey:
     def prove_msms_dev(self, d_wtns):
         out = ctypes.create_string_buffer(768)
         self.ctx._check(lib().b200_prove_msms_dev(self.ctx.handle, self.handle, _vp(d_wtns), out))
+        return out.raw
+
+    def prove_begin(self, wtns, on_device=False, poly_mask=7):
+        """Stage 1 of the two-stage prove (multi-GPU): -> ([d_a, d_b, d_c] device addresses, H-stream handle).
+        Returns without synchronising; exchange the buffers on that stream, then call prove_finish()."""
+        bufs = (_vp * 3)()
+        hs = _vp()
+        w = _vp(wtns) if on_device else _ptr(wtns)
+        self.ctx._check(lib().b200_prove_begin(self.ctx.handle, self.handle, w, 1 if on_device else 0, _u32(poly_mask),
+                                               bufs, ctypes.byref(hs)))
+        return [int(b or 0) for b in bufs], int(hs.value or 0)
+
+    def prove_finish(self):
+        out = ctypes.create_string_buffer(768)
+        self.ctx._check(lib().b200_prove_finish(self.ctx.handle, self.handle, out))
         return out.raw
 
     def free(self):

@@ -43,6 +43,11 @@ int b200_init(int device, b200_ctx **out) {
         int lo_p = 0, hi_p = 0;
         cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
         e = cudaStreamCreateWithPriority(&h->c.hstream, cudaStreamNonBlocking, hi_p);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = cudaStreamCreateWithPriority(&h->c.hstream_bc[i], cudaStreamNonBlocking, hi_p);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_h_join[i], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_h_fork, cudaEventDisableTiming);
         for (int i = 0; i < Ctx::MSM_SLOTS && e == cudaSuccess; i++)
             e = cudaStreamCreateWithPriority(&h->c.side[i], cudaStreamNonBlocking, hi_p);
     }
@@ -81,6 +86,8 @@ void b200_free(b200_ctx *h) {
     for (int i = 0; i < Ctx::MSM_SLOTS; i++) { if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_merge[i]) cudaEventDestroy(c->ev_merge[i]); }
     for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) cudaStreamDestroy(c->side[i]);
     if (c->hstream) cudaStreamDestroy(c->hstream);
+    for (int i = 0; i < 2; i++) { if (c->hstream_bc[i]) cudaStreamDestroy(c->hstream_bc[i]); if (c->ev_h_join[i]) cudaEventDestroy(c->ev_h_join[i]); }
+    if (c->ev_h_fork) cudaEventDestroy(c->ev_h_fork);
     if (c->ev_h) cudaEventDestroy(c->ev_h);
     cudaStreamDestroy(c->stream);
     delete h;
@@ -94,6 +101,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     if (!h || !name) return B200_ERR_ARG;
     if (!strcmp(name, "msm_window")) h->c.force_c = value;
     else if (!strcmp(name, "acc_smem")) h->c.opt_acc_smem = value;
+    else if (!strcmp(name, "h_streams")) h->c.opt_h_streams = value;
     else if (!strcmp(name, "g2_minb")) h->c.opt_g2_minb = value;
     else if (!strcmp(name, "g1_minb")) h->c.opt_g1_minb = value;
     else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;

@@ -35,6 +35,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t hstream = nullptr;    // H pipeline (a,b,c build + NTTs) overlapping the witness MSMs
     cudaEvent_t ev_h = nullptr;
+    cudaStream_t hstream_bc[2] = {nullptr, nullptr};   // b and c transform chains beside a's (opt_h_streams = 3)
+    cudaEvent_t ev_h_fork = nullptr, ev_h_join[2] = {nullptr, nullptr};
+    int opt_h_streams = 0;             // 0 auto (3 for sharded zkeys, where the H pipeline is the critical path), 1, 3
     static const int MSM_SLOTS = 8;    // in-flight MSM results; each slot owns a side stream and its bucket buffers
     cudaStream_t side[MSM_SLOTS] = {nullptr};   // folding + reduction of slot k's MSM run here (high priority) while
                                                 // the next MSMs sort / accumulate on `stream`

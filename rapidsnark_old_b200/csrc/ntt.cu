@@ -400,25 +400,60 @@ int ntt_natural(Ctx *ctx, Fr *d_a, uint64_t n, bool inverse) {
     return B200_OK;
 }
 
+static int h_scale_twist_k0(Ctx *ctx, Fr *d, const Fr &ninv, const NttTable &tf) {
+    B200_LAUNCH(ctx, k_ntt_scale_twist_brev, 1, 256, 0, d, 0, ninv, tf);
+    return B200_OK;
+}
+
 // a, b, c (natural order, Montgomery) -> h scalars in d_a (normal form)   (groth16.cpp:101-163)
-int h_pipeline(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n) {
+// nstreams = 3: the three transform chains are independent until the final combine; b and c run on their own
+// streams beside a's (forked from / joined into ctx->stream by events).  Same kernels, same results; it only
+// matters when the GPU is not already full (sharded zkeys: small MSMs, the H pipeline is the critical path).
+// poly_mask: bit i set = run the transform chain of arr[i] here (multi-GPU: the chains are spread over the ranks
+// and exchanged before the combine); combine = false leaves a, b, c as coset evaluations for that exchange.
+int h_transforms(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n, int nstreams, unsigned poly_mask) {
     int k = ilog2_exact(n);
     if (k < 0) { ctx->err = "h pipeline: domain size must be a power of two"; return B200_ERR_ARG; }
     if (k + 1 > 28) { ctx->err = "Domain size too big for the curve"; return B200_ERR_RANGE; }
-    NttTable tf;
+    NttTable tf, ti;
     B200_TRY(ntt_get_table(ctx, k, false, &tf));
+    if (k > 0) B200_TRY(ntt_get_table(ctx, k, true, &ti));   // built on ctx->stream before any fork
     Fr ninv = host_n_inv(k);
     Fr *arr[3] = {d_a, d_b, d_c};
-    for (int i = 0; i < 3; i++) {
-        if (k == 0) {
-            B200_LAUNCH(ctx, k_ntt_scale_twist_brev, 1, 256, 0, arr[i], k, ninv, tf);
-        } else {
-            B200_TRY(ntt_dif(ctx, arr[i], k, true, &ninv));    // ifft + 1/n + coset twist, output bit-reversed
+    cudaStream_t main_stream = ctx->stream;
+    const bool fork = nstreams >= 3 && ctx->hstream_bc[0] && ctx->hstream_bc[1];
+    if (fork) B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_h_fork, main_stream));
+    int rc = B200_OK;
+    for (int i = 0; i < 3 && rc == B200_OK; i++) {
+        if (!((poly_mask >> i) & 1u)) continue;
+        if (fork && i > 0) {
+            ctx->stream = ctx->hstream_bc[i - 1];
+            if (cudaStreamWaitEvent(ctx->stream, ctx->ev_h_fork, 0) != cudaSuccess) rc = B200_ERR_CUDA;
         }
-        B200_TRY(ntt_dit(ctx, arr[i], k, false));
+        if (rc == B200_OK) {
+            if (k == 0) rc = h_scale_twist_k0(ctx, arr[i], ninv, tf);
+            else rc = ntt_dif(ctx, arr[i], k, true, &ninv);    // ifft + 1/n + coset twist, output bit-reversed
+        }
+        if (rc == B200_OK) rc = ntt_dit(ctx, arr[i], k, false);
+        if (fork && i > 0) {
+            if (rc == B200_OK && cudaEventRecord(ctx->ev_h_join[i - 1], ctx->stream) != cudaSuccess) rc = B200_ERR_CUDA;
+            ctx->stream = main_stream;
+            if (rc == B200_OK && cudaStreamWaitEvent(main_stream, ctx->ev_h_join[i - 1], 0) != cudaSuccess) rc = B200_ERR_CUDA;
+        }
     }
+    ctx->stream = main_stream;
+    return rc;
+}
+
+// h[i] = fromMontgomery(a[i] * b[i] - c[i]) into d_a   (groth16.cpp:158-163)
+int h_combine(Ctx *ctx, Fr *d_a, const Fr *d_b, const Fr *d_c, uint64_t n) {
     B200_LAUNCH(ctx, k_h_combine, (u32)((n + 255) / 256), 256, 0, d_a, d_b, d_c, n);
     return B200_OK;
+}
+
+int h_pipeline(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n, int nstreams) {
+    B200_TRY(h_transforms(ctx, d_a, d_b, d_c, n, nstreams, 7u));
+    return h_combine(ctx, d_a, d_b, d_c, n);
 }
 
 int build_abc(Ctx *ctx, const Fr *d_wtns, const u32 *d_row_a, const u32 *d_row_b, const u32 *d_sig, const Fr *d_coef,

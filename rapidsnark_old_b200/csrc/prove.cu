@@ -12,7 +12,9 @@
 
 namespace b200 {
 int ntt_natural(Ctx *ctx, Fr *d_a, uint64_t n, bool inverse);
-int h_pipeline(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n);
+int h_pipeline(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n, int nstreams);
+int h_transforms(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n, int nstreams, unsigned poly_mask);
+int h_combine(Ctx *ctx, Fr *d_a, const Fr *d_b, const Fr *d_c, uint64_t n);
 int build_abc(Ctx *ctx, const Fr *d_wtns, const u32 *d_row_a, const u32 *d_row_b, const u32 *d_sig, const Fr *d_coef,
               u32 n, Fr *d_a, Fr *d_b, Fr *d_c);
 }  // namespace b200
@@ -27,6 +29,8 @@ struct b200_zkey {
     u32 n_vars, n_public, domain_size;
     u64 n_coefs;
     Range rA, rC, rH;       // this shard's index ranges (A, B1, B2 share rA)
+    bool stage1_done = false, stage1_combined = false;   // b200_prove_begin / b200_prove_finish pairing
+    bool sharded = false;   // shard_count > 1: small MSMs, the (replicated) H pipeline is the critical path
     u32 *d_row_a = nullptr, *d_row_b = nullptr, *d_sig = nullptr;
     Fr *d_coef = nullptr;
     G1Affine *d_A = nullptr, *d_B1 = nullptr, *d_C = nullptr, *d_H = nullptr;   // plain shard slices, or
@@ -218,6 +222,7 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     b200_zkey *zk = new b200_zkey();
     zk->ctx = c;
     zk->n_vars = d->n_vars; zk->n_public = d->n_public; zk->domain_size = n; zk->n_coefs = d->n_coefs;
+    zk->sharded = cnt > 1;
     zk->rA = shard_range(d->n_vars, d->shard_index, cnt);
     zk->rC = zk->rA;   // the C table is padded to the witness indexing (see below)
     zk->rH = shard_range(n, d->shard_index, cnt);
@@ -314,20 +319,25 @@ static int wtns_upload(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_dev
     return B200_OK;
 }
 
-// `after`: event on another stream the H pipeline has to wait for (witness uploaded / witness digits sorted)
-static int h_on_device(Ctx *c, b200_zkey *zk, bool overlap = false, cudaEvent_t after = nullptr) {
+// `after`: event on another stream the H pipeline has to wait for (witness uploaded / witness digits sorted).
+// poly_mask / combine: see h_transforms (ntt.cu); the single-GPU path runs all three chains and the combine.
+static int h_on_device(Ctx *c, b200_zkey *zk, bool overlap = false, cudaEvent_t after = nullptr, unsigned poly_mask = 7u,
+                       bool combine = true) {
     cudaStream_t main_stream = c->stream;
     if (overlap) {
         if (after) B200_CUDA_CHECK(c, cudaStreamWaitEvent(c->hstream, after, 0));
         c->stream = c->hstream;           // build_abc / h_pipeline launch on c->stream
     }
     int rc = B200_OK;
-    phase_begin(c, PH_BUILD_AB);
-    rc = build_abc(c, zk->d_wtns, zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->domain_size, zk->d_a, zk->d_b, zk->d_c);
-    phase_end(c);
-    if (rc == B200_OK) {
+    if (poly_mask) {                      // a rank that owns no chain receives all three polynomials
+        phase_begin(c, PH_BUILD_AB);
+        rc = build_abc(c, zk->d_wtns, zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->domain_size, zk->d_a, zk->d_b, zk->d_c);
+        phase_end(c);
+    }
+    if (rc == B200_OK && (poly_mask || combine)) {
         phase_begin(c, PH_NTT);
-        rc = h_pipeline(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size);
+        rc = h_transforms(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size, c->opt_h_streams ? c->opt_h_streams : 1, poly_mask);
+        if (rc == B200_OK && combine) rc = h_combine(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size);
         phase_end(c);
     }
     if (overlap) {
@@ -350,16 +360,15 @@ int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_ou
     return B200_OK;
 }
 
-static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bool wtns_on_device, void *out768) {
-    if (!h || !zk || !wtns_host || !out768) return B200_ERR_ARG;
-    Ctx *c = &h->c;
+// Stage 1: witness upload, the four witness MSMs enqueued, a/b/c built and the transform chains in poly_mask run on
+// the H stream.  Stage 2 (prove_stage2): combine, H MSM, collect.  A single GPU runs both back to back; with the
+// zkey sharded over several GPUs the caller exchanges the transformed polynomials between the stages (on the H
+// stream), each rank having run only the chains it owns.
+static int prove_stage1(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, unsigned poly_mask, bool combine) {
     cudaSetDevice(c->device);
     phase_reset(c);
-    B200_TRY(wtns_upload(c, zk, wtns_host, wtns_on_device));
+    B200_TRY(wtns_upload(c, zk, wtns, wtns_on_device));
     B200_CUDA_CHECK(c, cudaEventRecord(c->ev_h, c->stream));   // "witness uploaded"
-    uint8_t *o = (uint8_t *)out768;
-    G1Xyzz pih, pia, pib1, pic;
-    G2Xyzz pib;
     const uint8_t *w = (const uint8_t *)zk->d_wtns;
     // groth16.cpp:173 / :183 / :190 / :197 / :204, restricted to this shard's point range.  All five MSMs are
     // enqueued back to back (bucket reductions overlap the next accumulation on a side stream), then collected.
@@ -371,10 +380,31 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     B200_TRY(msm_g2_enqueue(c, zk->d_B2, w + zk->rA.lo * 32, 32, lenA, 1, &zk->tB2, false, false));
     // H pipeline on its own stream, started once the witness digits are sorted (the sort is atomics-bound and would
     // only be slowed down by the NTT kernels; the G2 accumulation that follows absorbs them)
-    B200_TRY(h_on_device(c, zk, true, lenA ? c->ev_sort[0] : c->ev_h));
+    B200_TRY(h_on_device(c, zk, true, lenA ? c->ev_sort[0] : c->ev_h, poly_mask, combine));
     B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom, false));
     B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom, false));
     B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom, false));
+    zk->stage1_done = true;
+    zk->stage1_combined = combine;
+    return B200_OK;
+}
+
+static int prove_stage2(Ctx *c, b200_zkey *zk, void *out768) {
+    if (!zk->stage1_done) { c->err = "prove_finish without prove_begin"; return B200_ERR_ARG; }
+    zk->stage1_done = false;
+    cudaSetDevice(c->device);
+    if (!zk->stage1_combined) {     // the exchanged a, b, c -> h, on the H stream behind the caller's exchange
+        cudaStream_t main_stream = c->stream;
+        c->stream = c->hstream;
+        phase_begin(c, PH_NTT);
+        int rc = h_combine(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size);
+        phase_end(c);
+        c->stream = main_stream;
+        B200_TRY(rc);
+    }
+    uint8_t *o = (uint8_t *)out768;
+    G1Xyzz pih, pia, pib1, pic;
+    G2Xyzz pib;
     // the digit sort of h runs on the H-pipeline stream right behind the NTTs (own sort workspace), i.e. under the
     // witness accumulations; only the H accumulation itself waits for it on the main stream
     B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true,
@@ -394,6 +424,28 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     memcpy(o + 384, &pib, 256);
     memcpy(o + 640, &pic, 128);
     return B200_OK;
+}
+
+static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bool wtns_on_device, void *out768) {
+    if (!h || !zk || !wtns_host || !out768) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    B200_TRY(prove_stage1(c, zk, wtns_host, wtns_on_device, 7u, true));
+    return prove_stage2(c, zk, out768);
+}
+
+int b200_prove_begin(b200_ctx *h, b200_zkey *zk, const void *wtns, int wtns_on_device, uint32_t poly_mask,
+                     void **d_abc3, void **h_stream) {
+    if (!h || !zk || !wtns || !d_abc3 || !h_stream) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    B200_TRY(prove_stage1(c, zk, wtns, wtns_on_device != 0, poly_mask & 7u, false));
+    d_abc3[0] = zk->d_a; d_abc3[1] = zk->d_b; d_abc3[2] = zk->d_c;
+    *h_stream = (void *)c->hstream;
+    return B200_OK;
+}
+
+int b200_prove_finish(b200_ctx *h, b200_zkey *zk, void *out768) {
+    if (!h || !zk || !out768) return B200_ERR_ARG;
+    return prove_stage2(&h->c, zk, out768);
 }
 
 int b200_prove_msms(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *out768) {

@@ -119,6 +119,41 @@ def test_sharded_proof_over_gloo_matches_golden(world):
     assert all(pr == C["proof"] for _, pr in res)
 
 
+def _exchange_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from rapidsnark_old_b200 import dist as bdist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    owners = bdist.poly_owners(world)
+    # every rank fills only the polynomials it owns (value = 10 * poly + owner), the rest is garbage
+    polys = [torch.full((64,), 10 * i + o if o == rank else 255, dtype=torch.uint8) for i, o in enumerate(owners)]
+    bdist.exchange_polys(polys)
+    q.put((rank, bdist.poly_mask(rank, world), [int(p[0]) for p in polys], [bool((p == p[0]).all()) for p in polys]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_h_polynomial_exchange_over_gloo(world):
+    """N > 1 host logic of the H-pipeline split: ownership masks cover a, b, c exactly once and one broadcast per
+    polynomial leaves every rank with all three (dist.exchange_polys; NCCL on the GPU box, gloo here)."""
+    import torch.multiprocessing as mp
+    from rapidsnark_old_b200 import dist as bdist
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    owners = bdist.poly_owners(world)
+    assert sum(m for _, m, _, _ in res) == 7 and all((res[o][1] >> i) & 1 for i, o in enumerate(owners))
+    for _, _, vals, uniform in res:
+        assert vals == [10 * i + o for i, o in enumerate(owners)] and all(uniform)
+
+
 # ----------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def gctx():

@@ -281,6 +281,49 @@ def test_sharded_prove_folds_to_unsharded(ctx, orc, shards):
     assert orc.msms_to_affine(folded) == synth_util.expected_affine(orc, s)
 
 
+def test_two_stage_prove_equals_one_call(ctx, orc):
+    """b200_prove_begin(poly_mask = 7) + b200_prove_finish is b200_prove_msms."""
+    s = synth_util.make(10)
+    wt = s.wtns_bytes()
+    zk = _upload(ctx, s)
+    one = zk.prove_msms(wt)
+    bufs, hstream = zk.prove_begin(wt, False, 7)
+    assert all(bufs) and hstream
+    two = zk.prove_finish()
+    assert orc.msms_to_affine(one) == orc.msms_to_affine(two) == synth_util.expected_affine(orc, s)
+    with pytest.raises(b200.B200Error):
+        zk.prove_finish()                      # no begin pending
+    zk.free()
+
+
+@pytest.mark.parametrize("shards", [2, 3, 5])
+def test_h_pipeline_spread_over_ranks(orc, shards):
+    """The N > 1 flow of dist.prove_msms_distributed on ONE device: every rank is its own context with its own
+    shard, runs only the transform chains it owns (dist.poly_mask), the three polynomials are then copied from
+    their owners to everybody (what the NCCL broadcasts do), and the folded partials equal the unsharded result."""
+    import torch
+    from rapidsnark_old_b200 import dist as bdist
+    s = synth_util.make(10)
+    wt = s.wtns_bytes()
+    ctxs = [b200.Context(0) for _ in range(shards)]
+    zks = [_upload(c, s, i, shards) for i, c in enumerate(ctxs)]
+    begun = [zk.prove_begin(wt, False, bdist.poly_mask(i, shards)) for i, zk in enumerate(zks)]
+    dev = torch.device("cuda", 0)
+    views = [[torch.as_tensor(bdist._DeviceBytes(ptr, s.n * 32), device=dev) for ptr in bufs] for bufs, _ in begun]
+    for _, hs in begun:
+        torch.cuda.ExternalStream(hs, device=dev).synchronize()
+    for poly, owner in enumerate(bdist.poly_owners(shards)):
+        for r in range(shards):
+            if r != owner:
+                views[r][poly].copy_(views[owner][poly])
+    torch.cuda.synchronize()
+    parts = [zk.prove_finish() for zk in zks]
+    assert orc.msms_to_affine(b200.fold_partials(parts)) == synth_util.expected_affine(orc, s)
+    for zk, c in zip(zks, ctxs):
+        zk.free()
+        c.close()
+
+
 def test_zkey_upload_rejects_bad_records(ctx):
     s = synth_util.make(4)
     p = s.points

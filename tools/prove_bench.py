@@ -30,10 +30,12 @@ def main():
     coefs = s.coefs_section()
     for cfg in args.configs:
         opts = dict(kv.split("=") for kv in cfg.split(",") if kv)
-        for k in ("precomp", "precomp_c", "acc_smem", "msm_window", "target_tasks_log2"):
+        for k in ("precomp", "precomp_c", "acc_smem", "msm_window", "target_tasks_log2", "h_streams", "g1_minb", "g2_minb"):
             ctx.set_option(k, int(opts.get(k, -1 if k in ("precomp", "acc_smem") else 0)))
+        shards = int(opts.get("shards", 1))     # this GPU plays rank 0 of `shards` (per-rank time of an N-GPU run)
         t0 = time.time()
-        zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"])
+        zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"],
+                             0, shards)
         up = time.time() - t0
         for _ in range(2):
             zk.prove_msms_dev(wt_dev.data_ptr())
