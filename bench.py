@@ -28,6 +28,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA call (see rapidsnark_old_b200/__init__.py)
 
 METRIC = "groth16_proof_ms_2^20_constraints"   # --log-n K renames it to ..._2^K_...
 UNIT = "ms"

@@ -13,6 +13,10 @@ Interface mirrored (reference iden3/rapidsnark-old):
 import ctypes
 import os
 
+# more hardware work queues than the default 8, so that the library's streams (main, H, one per in-flight MSM) and
+# torch's / NCCL's never share one and serialise; only effective before the process's first CUDA call
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libb200snark.so")   # B200_LIB: A/B builds of the same ABI
 

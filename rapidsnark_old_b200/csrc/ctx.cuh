@@ -35,6 +35,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t hstream = nullptr;    // H pipeline (a,b,c build + NTTs) overlapping the witness MSMs
     cudaEvent_t ev_h = nullptr;
+    int hi_prio = 0;                   // stream priority of the side / H streams
     cudaStream_t hstream_bc[2] = {nullptr, nullptr};   // b and c transform chains beside a's (opt_h_streams = 3)
     cudaEvent_t ev_h_fork = nullptr, ev_h_join[2] = {nullptr, nullptr};
     int opt_h_streams = 0;             // 0 auto (3 for sharded zkeys, where the H pipeline is the critical path), 1, 3
@@ -49,6 +50,8 @@ struct Ctx {
     int sm_count = 148;
     int force_c = 0;
     int opt_acc_smem = -1;   // -1 auto, 0 registers, 1 shared memory (experiments)
+    int opt_reduce_l = 0, opt_reduce_l_g2 = 0;   // 0 = automatic segment length of the bucket reduction
+    int opt_warm_max = 0;    // 0 = default (msm.cuh MSM_WARM_MAX)
     int opt_g1_minb = 0;     // 0 auto; 3 / 4 for the G1 accumulation (168 / 128 registers)
     int opt_g2_minb = 0;     // 0 auto; 2 / 3: resident CTAs per SM the G2 accumulation is compiled for (255 / 168 registers)
     int opt_precomp = -1;    // -1 auto (on), 0 off; window bits of resident tables in opt_precomp_c
@@ -121,6 +124,12 @@ inline int ctx_pinned(Ctx *ctx, size_t bytes) {
     B200_CUDA_CHECK(ctx, cudaMallocHost(&ctx->pinned, bytes));
     ctx->pinned_cap = bytes;
     return B200_OK;
+}
+
+// side streams are created on first use (see b200_init)
+inline cudaStream_t ctx_side_stream(Ctx *ctx, int slot) {
+    if (!ctx->side[slot]) cudaStreamCreateWithPriority(&ctx->side[slot], cudaStreamNonBlocking, ctx->hi_prio);
+    return ctx->side[slot];
 }
 
 // phase timers: CUDA events on the ctx stream around each phase; collected after the final sync

@@ -56,7 +56,8 @@ struct MsmGeom {
 static const u32 MSM_MAX_BATCH = 1u << 24;   // points per sort batch (entries < 2^32, entry index < 2^31)
 static const int MSM_MAX_WIN = 65;
 static const u32 MSM_TARGET_TASKS = 1u << 18;
-static const u32 MSM_WARM_MAX = 64;          // buckets cut into <= 64 tasks are folded by one thread, more by a CTA
+static const u32 MSM_WARM_MAX = 8;           // buckets cut into <= 8 tasks are folded by one thread (a serial chain), more by a
+                                             // CTA tree (option "warm_max"; 64 made the 2-GPU shards' narrow top window a 64-add chain)
 static const u32 MSM_MAX_CAP = 2048;         // task-length histogram has MSM_MAX_CAP + 1 <= 4096 bins
 
 inline int msm_auto_c(uint64_t n) {
@@ -89,6 +90,9 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     // reduce segments: longer for big bucket sets (amortises the per-segment multiplier, keeps the side-stream
     // kernel's footprint to a few dozen CTAs)
     g.L = g.nbk >= (1u << 18) ? 64 : g.nbk >= (1u << 17) ? 32 : g.nbk >= 16 ? 16 : g.nbk;
+    // one shared bucket set (resident tables) below 2^19 buckets = a shard of a multi-GPU zkey: the accumulations
+    // are short, the reduction chains are what the proof waits for (measured at 2 / 4 shards: 16 beats 64 by 7 %)
+    if (shared_buckets && g.nbk < (1u << 19) && g.L > 16) g.L = 16;
     if (tail && g.L > 16) g.L = 16;   // nothing left to overlap with: shortest chains, the whole GPU is free
     g.nseg = g.nbk / g.L;
     g.nplanes = 0;
@@ -240,7 +244,7 @@ static __global__ void __launch_bounds__(1024) k_scan_add(u32 *__restrict__ data
 static __global__ void __launch_bounds__(256) k_msm_plan_count(const u32 *__restrict__ off, u32 NB, u32 CAP,
                                                           u32 *__restrict__ lenhist /* [4096], index CAP_MAX - len */,
                                                           u32 *__restrict__ plan, u32 *__restrict__ hot_base,
-                                                          u32 *__restrict__ hot_list, u32 *__restrict__ warm_list) {
+                                                          u32 *__restrict__ hot_list, u32 *__restrict__ warm_list, u32 warm_max) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= NB) return;
     u32 cnt = off[b + 1] - off[b];
@@ -251,7 +255,7 @@ static __global__ void __launch_bounds__(256) k_msm_plan_count(const u32 *__rest
     u32 ntask = nfull + (rem ? 1u : 0u);
     if (ntask > 1) {
         hot_base[b] = atomicAdd(&plan[0], ntask);
-        if (ntask > MSM_WARM_MAX) hot_list[atomicAdd(&plan[1], 1u)] = b;
+        if (ntask > warm_max) hot_list[atomicAdd(&plan[1], 1u)] = b;
         else warm_list[atomicAdd(&plan[3], 1u)] = b;
     }
 }
@@ -562,6 +566,15 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     int c = pre ? table->c : msm_auto_c(n);
     if (!pre && ctx->force_c >= 4 && ctx->force_c <= 20) c = ctx->force_c;
     MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre, ctx->opt_target_tasks_log2, tail);
+    {   // experiments: reduce-segment length override ("reduce_l" both groups, "reduce_l_g2" G2 only); power of two
+        int ov = (sizeof(F) != 32 && ctx->opt_reduce_l_g2 > 0) ? ctx->opt_reduce_l_g2 : ctx->opt_reduce_l;
+        if (ov > 0 && (ov & (ov - 1)) == 0 && (u32)ov <= g.nbk && !(tail && ov > 16)) {
+            g.L = (u32)ov;
+            g.nseg = g.nbk / g.L;
+            g.nplanes = 0;
+            while ((1u << g.nplanes) < g.nseg) g.nplanes++;
+        }
+    }
     if (g.nwin > MSM_MAX_WIN) { ctx->err = "msm: too many windows"; return B200_ERR_ARG; }
     if (pre && (uint64_t)g.nwin * n >= (1ull << 31)) { ctx->err = "msm: table too large for 31-bit entries"; return B200_ERR_ARG; }
     if (reuse_sort && (n > batch_max)) { ctx->err = "msm: reuse_sort needs a single batch"; return B200_ERR_ARG; }
@@ -600,7 +613,8 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     Pt *d_segs = (Pt *)ctx->w_segs[bb].p;
     Pt *d_win = (Pt *)((uint8_t *)ctx->w_win.p + (size_t)slot * MSM_SLOT_PTS * PT_MAX);
     Pt *h_win = (Pt *)((uint8_t *)ctx->pinned + (size_t)slot * MSM_SLOT_PTS * PT_MAX);
-    cudaStream_t st = ctx->stream, side = ctx->side[slot];
+    cudaStream_t st = ctx->stream, side = ctx_side_stream(ctx, slot);
+    if (!side) { ctx->err = "msm: cannot create the side stream"; return B200_ERR_CUDA; }
     const bool g2 = sizeof(F) != 32;
     const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
     const size_t acc_smem_bytes = 128 * sizeof(Pt);
@@ -639,7 +653,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             B200_LAUNCH_ON(ctx, ss, k_scan_add, ntiles, 1024, 0, d_hist, d_totals, d_cursor);
             B200_LAUNCH_ON(ctx, ss, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_cursor, d_entries);
             // task plan: histogram of task lengths (descending), scan, placement
-            B200_LAUNCH_ON(ctx, ss, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list, d_warm_list);
+            B200_LAUNCH_ON(ctx, ss, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list, d_warm_list, ctx->opt_warm_max > 0 ? (u32)ctx->opt_warm_max : MSM_WARM_MAX);
             B200_LAUNCH_ON(ctx, ss, k_scan_tile, 1, 1024, 0, d_lenhist, d_plan + 2);      // d_plan[2] = number of tasks
             B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, ss));
             B200_LAUNCH_ON(ctx, ss, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);

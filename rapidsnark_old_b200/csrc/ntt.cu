@@ -421,6 +421,9 @@ int h_transforms(Ctx *ctx, Fr *d_a, Fr *d_b, Fr *d_c, uint64_t n, int nstreams, 
     Fr ninv = host_n_inv(k);
     Fr *arr[3] = {d_a, d_b, d_c};
     cudaStream_t main_stream = ctx->stream;
+    if (nstreams >= 3)
+        for (int i = 0; i < 2; i++)
+            if (!ctx->hstream_bc[i]) cudaStreamCreateWithPriority(&ctx->hstream_bc[i], cudaStreamNonBlocking, ctx->hi_prio);
     const bool fork = nstreams >= 3 && ctx->hstream_bc[0] && ctx->hstream_bc[1];
     if (fork) B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_h_fork, main_stream));
     int rc = B200_OK;

@@ -415,7 +415,7 @@ static int prove_stage2(Ctx *c, b200_zkey *zk, void *out768) {
     B200_TRY(msm_g1_collect(c, 3, &pib1));
     B200_TRY(msm_g1_collect(c, 4, &pic));
     B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < Ctx::MSM_SLOTS; i++) B200_CUDA_CHECK(c, cudaStreamSynchronize(c->side[i]));
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) B200_CUDA_CHECK(c, cudaStreamSynchronize(c->side[i]));
     B200_CUDA_CHECK(c, cudaStreamSynchronize(c->hstream));
     phase_collect(c);
     memcpy(o, &pih, 128);
