@@ -105,6 +105,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "acc_smem")) h->c.opt_acc_smem = value;
     else if (!strcmp(name, "h_streams")) h->c.opt_h_streams = value;
     else if (!strcmp(name, "warm_max")) h->c.opt_warm_max = value;
+    else if (!strcmp(name, "tree_threads")) h->c.opt_tree_threads = (value == 32 || value == 64 || value == 128) ? value : 0;
     else if (!strcmp(name, "reduce_l")) h->c.opt_reduce_l = value;
     else if (!strcmp(name, "reduce_l_g2")) h->c.opt_reduce_l_g2 = value;
     else if (!strcmp(name, "g2_minb")) h->c.opt_g2_minb = value;

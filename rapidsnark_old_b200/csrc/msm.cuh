@@ -616,6 +616,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     cudaStream_t st = ctx->stream, side = ctx_side_stream(ctx, slot);
     if (!side) { ctx->err = "msm: cannot create the side stream"; return B200_ERR_CUDA; }
     const bool g2 = sizeof(F) != 32;
+    const u32 tree_threads = ctx->opt_tree_threads > 0 ? (u32)ctx->opt_tree_threads : (g2 ? 64u : 128u);
     const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
     const size_t acc_smem_bytes = 128 * sizeof(Pt);
     static const int env_g2_minb = getenv("B200_G2_MINB") ? atoi(getenv("B200_G2_MINB")) : 0;   // experiments
@@ -688,8 +689,11 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(side, ctx->ev_acc[slot], 0));
         }
         phase_begin(ctx, PH_MSM_MERGE, ms);
-        B200_LAUNCH_ON(ctx, ms, k_msm_merge_warm<F>, 4 * ctx->sm_count, 128, 0, d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_warm_list);
-        B200_LAUNCH_ON(ctx, ms, k_msm_merge_hot<F>, 2 * ctx->sm_count, 128, 128 * sizeof(Pt), d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_hot_list);
+        // side-stream kernels keep a CTA's register footprint at or below one G1 accumulation CTA (128 x 128
+        // registers), otherwise they only get onto an SM when two of those retire together: 32-thread CTAs for the
+        // per-thread folds, 64-thread trees for G2 (168 registers per thread)
+        B200_LAUNCH_ON(ctx, ms, k_msm_merge_warm<F>, 16 * ctx->sm_count, 32, 0, d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_warm_list);
+        B200_LAUNCH_ON(ctx, ms, k_msm_merge_hot<F>, 2 * ctx->sm_count, tree_threads, tree_threads * sizeof(Pt), d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_hot_list);
         phase_end(ctx, ms);
         if (last_batch) {
             B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_merge[slot], side));
@@ -705,8 +709,8 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
         u32 nchunk = (g.nseg + 1023) / 1024;
         if (nchunk > 128) nchunk = 128;
         Pt *d_chunk = d_segs + 2 * (size_t)total_segs;
-        B200_LAUNCH_ON(ctx, side, k_msm_plane_sum<F>, dim3(nchunk, npl1, g.nwin_b), 128, 128 * sizeof(Pt), d_segs, g.nseg, nchunk, g.nplanes, d_chunk);
-        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, npl1 * g.nwin_b), 128, 128 * sizeof(Pt), d_chunk, nchunk, 1u, d_win);
+        B200_LAUNCH_ON(ctx, side, k_msm_plane_sum<F>, dim3(nchunk, npl1, g.nwin_b), tree_threads, tree_threads * sizeof(Pt), d_segs, g.nseg, nchunk, g.nplanes, d_chunk);
+        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, npl1 * g.nwin_b), tree_threads, tree_threads * sizeof(Pt), d_chunk, nchunk, 1u, d_win);
     }
     phase_end(ctx, side);
     B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * npl1 * sizeof(Pt), cudaMemcpyDeviceToHost, side));

@@ -46,6 +46,24 @@ static Range shard_range(uint64_t len, u32 idx, u32 cnt) {
     return r;
 }
 
+// Window width of the resident tables for `len` points: the zkey's scalars (witness, h) are field elements below
+// r < 2^254, so ceil(254 / c) windows carry digits; cost = one mixed addition per digit plus two full additions
+// (~2.8 mixed) per bucket of the shared set.  Widths that leave only a few bits for the top window are penalised:
+// they pile len / 2^bits entries on each of a handful of buckets, whose partial sums then fold through long
+// serial chains (c = 18: 2 bits, c = 19: 7 bits - measured at 4 and 2 shards of a 2^20 circuit).  2^20 points -> 20
+// (measured best of 16..20 on B200), 2^17..2^19 -> 17.  Any width gives the same result.
+static int table_window_bits(uint64_t len) {
+    int best = 11;
+    double best_cost = 0;
+    for (int cb = 11; cb <= 20; cb++) {
+        const int eff = (254 + cb - 1) / cb, top_bits = 254 - cb * (eff - 1);
+        double cost = (double)eff * (double)len + 2.8 * (double)(1u << (cb - 1));
+        if (top_bits <= 8) cost += 0.1 * (double)len;
+        if (cb == 11 || cost < best_cost) { best = cb; best_cost = cost; }
+    }
+    return best;
+}
+
 template <class T>
 static int upload_slice(Ctx *c, T **dst, const void *src, Range r) {
     size_t cnt = (size_t)(r.hi - r.lo);
@@ -259,7 +277,7 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
         uint64_t len_max = std::max<uint64_t>(zk->rA.hi - zk->rA.lo, zk->rH.hi - zk->rH.lo);
         int lg = 0;
         while ((2ull << lg) <= len_max) lg++;
-        int pc = c->opt_precomp_c > 0 ? c->opt_precomp_c : std::min(20, std::max(11, lg));
+        int pc = c->opt_precomp_c > 0 ? c->opt_precomp_c : table_window_bits(len_max);
         if (c->opt_precomp_c <= 0 && lg < 11) pc = 0;
         int rows = pc > 0 ? msm_table_windows(pc) : 0;
         uint64_t lenA = zk->rA.hi - zk->rA.lo, lenC = lenA, lenH = zk->rH.hi - zk->rH.lo;
