@@ -28,17 +28,28 @@ def main():
     ap.add_argument("--scalars", default="full", choices=["full", "fr"])
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--acc-smem", type=int, default=-1)
+    ap.add_argument("--cpu-max-log-n", type=int, default=0,
+                    help="also time the reference's CPU multiexp (oracle/_ref, all host cores) up to this size (1 GPU runs only)")
     args = ap.parse_args()
-    ctx = b200.Context(0)
+    # under torchrun (WORLD_SIZE > 1): the points are sharded by range over the ranks, each rank runs the MSM of its
+    # slice, the 128 / 256-byte partial sums are all_gathered (NCCL) and folded on the host; time = max over ranks
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = b200.Context(local)
     if args.c:
         ctx.set_msm_window(args.c)
     ctx.set_option("acc_smem", args.acc_smem)
-    stream = torch.cuda.ExternalStream(ctx.stream())
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     for log_n in args.log_n:
-        n = 1 << log_n
-        rng = np.random.default_rng(5)
+        n_total = 1 << log_n
+        n = n_total * (rank + 1) // world - n_total * rank // world      # this rank's slice
+        rng = np.random.default_rng(5 + rank)
         # distinct bases from a pool of 2^20 (larger n repeats the pool: same arithmetic cost, bounded setup)
         pool = min(n, 1 << 20)
+        psz_out = 256 if args.g2 else 128
         ks = rng.integers(0, 1 << 63, size=(pool, 4), dtype=np.uint64)
         ks[:, 3] &= (1 << 60) - 1
         g = synth.g2_gen_bytes() if args.g2 else synth.g1_gen_bytes()
@@ -54,7 +65,7 @@ def main():
         d_sc = torch.from_numpy(sc.view(np.uint8).reshape(-1).copy()).cuda()
         run = ctx.msm_g2_dev if args.g2 else ctx.msm_g1_dev
         out = run(d_bases.data_ptr(), d_sc.data_ptr(), n)      # warm-up + optional check
-        if args.check and n <= (1 << 20):
+        if args.check and n <= (1 << 20) and world == 1:
             R = synth.R
             kk = [int.from_bytes(ks[i].tobytes(), "little") for i in range(pool)]
             ss = [int.from_bytes(sc[i].tobytes(), "little") for i in range(n)]
@@ -63,24 +74,56 @@ def main():
                 assert b200.host_g2_to_affine(out) == b200.host_g2_to_affine(b200.host_g2_mul(g, tot.to_bytes(32, "little")))
             else:
                 assert b200.host_g1_to_affine(out) == b200.host_g1_to_affine(b200.host_g1_mul(g, tot.to_bytes(32, "little")))
+        def step():
+            part = run(d_bases.data_ptr(), d_sc.data_ptr(), n)
+            if world > 1:
+                mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).cuda()
+                outs = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(outs, mine)
+                acc = bytes(outs[0].cpu().numpy())
+                for o in outs[1:]:
+                    acc = (b200.host_g2_add if args.g2 else b200.host_g1_add)(acc, bytes(o.cpu().numpy()))
+                return acc
+            return part
         for _ in range(2):
-            run(d_bases.data_ptr(), d_sc.data_ptr(), n)
+            step()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         phases = {}
         e0.record(stream)
         for _ in range(args.iters):
-            run(d_bases.data_ptr(), d_sc.data_ptr(), n)
+            step()
             for k, v in ctx.phase_ms().items():
                 phases[k] = phases.get(k, 0.0) + v / args.iters
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
-        print(json.dumps({"group": "G2" if args.g2 else "G1", "log_n": log_n, "ms": round(ms, 4),
-                          "points_per_s": round(n / ms * 1e3), "scalars": args.scalars, "c": args.c or "auto",
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        cpu = None
+        if world == 1 and log_n <= args.cpu_max_log_n:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib
+            o = oracle_lib.ref() or oracle_lib.port()
+            hb, hs = bytes(d_bases.cpu().numpy()), bytes(d_sc.cpu().numpy())
+            t0 = time.perf_counter()
+            ref_out = (o.g2_msm if args.g2 else o.g1_msm)(hb, hs, n)
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            same = (o.g2_to_affine if args.g2 else o.g1_to_affine)(ref_out) == (o.g2_to_affine if args.g2 else o.g1_to_affine)(out)
+            cpu = {"ms": round(cpu_ms, 1), "points_per_s": round(n / cpu_ms * 1e3), "cores": o.threads(), "kind": o.kind,
+                   "same_point_as_gpu": bool(same)}
+        if rank == 0:
+            print(json.dumps({"group": "G2" if args.g2 else "G1", "log_n": log_n, "n_gpus": world, "ms": round(ms, 4), "cpu": cpu,
+                          "points_per_s": round(n_total / ms * 1e3), "scalars": args.scalars, "c": args.c or "auto",
                           "phases_ms": {k: round(v, 4) for k, v in phases.items() if v > 0}}), flush=True)
         del d_bases, d_sc
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
