@@ -1,4 +1,7 @@
-// scratch check: new field products vs the word-serial one, on the host build of field.cuh
+// Bit-exactness of the build-time product variants of csrc/field.cuh / fq2.cuh (B200_KARATSUBA, B200_LAZY_PAIR) against
+// the word-serial Montgomery product, on the HOST build of the very same source (carry flag emulated, bigint.cuh).
+//   g++ -O2 -std=c++17 -DB200_KARATSUBA=K -DB200_LAZY_PAIR=L -x c++ host_test.cpp -o t && ./t [iterations]
+// Run for all four (K, L) by tests/test_host_cpu.py.
 #include "../../rapidsnark_old_b200/csrc/curve.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -55,4 +58,7 @@ int run2(long iters) {
     printf("Fq2: bad=%ld\n", bad);
     return bad != 0;
 }
-int main() { return run<Fq>("Fq", 1000000) | run<Fr>("Fr", 1000000) | run2(1000000); }
+int main(int argc, char **argv) {
+    long it = argc > 1 ? atol(argv[1]) : 1000000;
+    return run<Fq>("Fq", it) | run<Fr>("Fr", it) | run2(it);
+}

@@ -1,4 +1,6 @@
-// scratch: instruction mix of one mixed addition / one product under the build-time variants of field.cuh
+// Instruction mix of one mixed addition / one product under the build-time variants of field.cuh:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DB200_KARATSUBA=K -DB200_LAZY_PAIR=L -cubin -o v.cubin sass.cu
+//   python sass_mix.py v.cubin "k_madd|k_mul|k_sqr"      (counts per pipe of the hot loop; no GPU needed)
 #include "../../rapidsnark_old_b200/csrc/curve.cuh"
 using namespace b200;
 template <class F>
