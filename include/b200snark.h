@@ -66,7 +66,8 @@ int b200_msm_g2_dev(b200_ctx *ctx, const void *d_bases_affine, const void *d_sca
 void b200_set_msm_window(b200_ctx *ctx, int c_bits);
 /* tuning knobs for experiments: "msm_window", "acc_smem" (-1 auto / 0 registers / 1 shared memory),
  * "precomp" (-1 auto / 0 off / 1 on: per-window precomputed tables for resident zkeys), "precomp_c",
- * "h_streams" (1 / 3: a, b, c transform chains on one or three streams), "g1_minb", "g2_minb" */
+ * "h_streams" (1 / 3: a, b, c transform chains on one or three streams), "g2_minb", "warm_max", "reduce_l",
+ * "reduce_l_g2", "tree_threads" */
 int b200_set_option(b200_ctx *ctx, const char *name, int value);
 
 /* ---- NTT: replaces FFT<Fr>::fft / ifft (fft.hpp:24-25), natural order in and out ------------------ */

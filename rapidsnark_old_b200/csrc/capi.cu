@@ -109,7 +109,6 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "reduce_l")) h->c.opt_reduce_l = value;
     else if (!strcmp(name, "reduce_l_g2")) h->c.opt_reduce_l_g2 = value;
     else if (!strcmp(name, "g2_minb")) h->c.opt_g2_minb = value;
-    else if (!strcmp(name, "g1_minb")) h->c.opt_g1_minb = value;
     else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;
     else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;
     else if (!strcmp(name, "target_tasks_log2")) h->c.opt_target_tasks_log2 = value;

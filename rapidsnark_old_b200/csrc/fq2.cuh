@@ -188,12 +188,92 @@ template <class B> HD_COLD Fq2T<B> csqr(const Fq2T<B> &x) { return fsqr(x); }
 template <class F> HD F cmul_sub_mul(const F &x, const F &y, const F &z, const F &w) { return fmul_sub_mul(x, y, z, w); }
 template <class B> HD_COLD Fq2T<B> cmul_sub_mul(const Fq2T<B> &x, const Fq2T<B> &y, const Fq2T<B> &z, const Fq2T<B> &w) { return fmul_sub_mul(x, y, z, w); }
 
-// Products of the HOT mixed addition.  B200_G2_HOT_CALLS = 1 routes the Fq2 ones through the out-of-line copies
-// too (operands through the local-memory stack): ~3x less code in the G2 accumulation loop, fewer live registers.
+// Products of the HOT mixed addition.  The G2 loop is ~100 KB of straight-line SASS when everything is inlined and
+// ncu attributes a quarter of its issue stalls to instruction fetch, so two out-of-line forms were built and
+// measured on B200 (2^20 proof, G2 accumulation phase 7.8 ms inlined):
+//   B200_G2_HOT_CALLS = 1  Fq2 products through the out-of-line cold copies (operands via the local-memory stack): 10.3 ms
+//   B200_G2_HOT_CALLS = 2  base-field product / reduction as by-value calls (operands in registers, loop 45 KB):  8.5 ms
+// Both lose to the inlined loop (0, the default); they stay as build variants for the record.
 #ifndef B200_G2_HOT_CALLS
 #define B200_G2_HOT_CALLS 0
 #endif
-#if B200_G2_HOT_CALLS
+#if B200_G2_HOT_CALLS == 2 && defined(__CUDA_ARCH__)
+// Variant 2: the Fq2 products of the hot loop are assembled from two out-of-line base-field routines whose
+// operands and results travel BY VALUE in registers (no stack traffic): the 512-bit product and the Montgomery
+// reduction.  One copy of each in the kernel image instead of ~46 inlined ones per mixed addition.
+struct W16 { u32 v[16]; };
+static __device__ __noinline__ W16 fq_mul_wide_call(Fq a, Fq b) { W16 r; detail::mul8x8(r.v, a.v, b.v); return r; }
+static __device__ __noinline__ Fq fq_reduce_call(W16 t) { Fq r; detail::mont_reduce16<FqParams>(r.v, t.v); fp_reduce_once(r); return r; }
+DEVFN Fq fq_add_noreduce(const Fq &a, const Fq &b) {
+    Fq r;
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+    r.v[7] = addc(a.v[7], b.v[7]);
+    return r;
+}
+DEVFN void w16_sub(W16 &t, const W16 &s) {        // t -= s, never negative
+    t.v[0] = sub_cc(t.v[0], s.v[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) t.v[i] = subc_cc(t.v[i], s.v[i]);
+    t.v[15] = subc(t.v[15], s.v[15]);
+}
+DEVFN u32 w16_sub_sign(W16 &t, const W16 &s) {    // t -= s mod 2^512, returns all-ones when negative
+    t.v[0] = sub_cc(t.v[0], s.v[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) t.v[i] = subc_cc(t.v[i], s.v[i]);
+    return subc(0, 0);
+}
+DEVFN void w16_add_p_hi(W16 &t, u32 mask) {       // t += (mask & p) * 2^256
+    t.v[8] = add_cc(t.v[8], mask & FqParams::mod(0));
+#pragma unroll
+    for (int i = 1; i < 7; i++) t.v[8 + i] = addc_cc(t.v[8 + i], mask & FqParams::mod(i));
+    t.v[15] = addc(t.v[15], mask & FqParams::mod(7));
+}
+// c0 = a0 b0 - a1 b1 (mod 2^512, sign returned), c1 = a0 b1 + a1 b0
+DEVFN u32 fq2_mul_wide_calls(W16 &c0, W16 &c1, const Fq2 &x, const Fq2 &y) {
+    c0 = fq_mul_wide_call(x.a, y.a);
+    W16 t1 = fq_mul_wide_call(x.b, y.b);
+    c1 = fq_mul_wide_call(fq_add_noreduce(x.a, x.b), fq_add_noreduce(y.a, y.b));
+    w16_sub(c1, c0);
+    w16_sub(c1, t1);
+    return w16_sub_sign(c0, t1);
+}
+DEVFN Fq2 hmul(const Fq2 &x, const Fq2 &y) {
+    W16 c0, c1;
+    u32 neg = fq2_mul_wide_calls(c0, c1, x, y);
+    w16_add_p_hi(c0, neg);
+    Fq2 r;
+    r.a = fq_reduce_call(c0);
+    r.b = fq_reduce_call(c1);
+    return r;
+}
+DEVFN Fq2 hsqr(const Fq2 &x) {
+    Fq2 r;
+    r.a = fq_reduce_call(fq_mul_wide_call(fadd(x.a, x.b), fsub(x.a, x.b)));
+    r.b = fdbl(fq_reduce_call(fq_mul_wide_call(x.a, x.b)));
+    return r;
+}
+DEVFN Fq2 hmul_sub_mul(const Fq2 &x, const Fq2 &y, const Fq2 &z, const Fq2 &w) {
+    W16 c0, c1, d0, d1;
+    u32 neg0 = fq2_mul_wide_calls(c0, c1, x, y);
+    u32 negd = fq2_mul_wide_calls(d0, d1, z, w);
+    c0.v[0] = sub_cc(c0.v[0], d0.v[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) c0.v[i] = subc_cc(c0.v[i], d0.v[i]);
+    u32 s0 = subc(neg0, negd);
+    w16_add_p_hi(c0, s0);
+    u32 s1 = w16_sub_sign(c1, d1);
+    w16_add_p_hi(c1, s1);
+    Fq2 r;
+    r.a = fq_reduce_call(c0);
+    r.b = fq_reduce_call(c1);
+    return r;
+}
+DEVFN Fq hmul(const Fq &x, const Fq &y) { return fmul(x, y); }
+DEVFN Fq hsqr(const Fq &x) { return fsqr(x); }
+DEVFN Fq hmul_sub_mul(const Fq &x, const Fq &y, const Fq &z, const Fq &w) { return fmul_sub_mul(x, y, z, w); }
+#elif B200_G2_HOT_CALLS == 1
 template <class F> HD F hmul(const F &x, const F &y) { return cmul(x, y); }
 template <class F> HD F hsqr(const F &x) { return csqr(x); }
 template <class F> HD F hmul_sub_mul(const F &x, const F &y, const F &z, const F &w) { return cmul_sub_mul(x, y, z, w); }

@@ -620,8 +620,6 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
     const size_t acc_smem_bytes = 128 * sizeof(Pt);
     static const int env_g2_minb = getenv("B200_G2_MINB") ? atoi(getenv("B200_G2_MINB")) : 0;   // experiments
-    static const int env_g1_minb = getenv("B200_G1_MINB") ? atoi(getenv("B200_G1_MINB")) : 0;
-    const int g1_minb = ctx->opt_g1_minb ? ctx->opt_g1_minb : env_g1_minb ? env_g1_minb : 3;
     const int g2_minb = ctx->opt_g2_minb ? ctx->opt_g2_minb : env_g2_minb ? env_g2_minb : (B200_G2_HOT_CALLS ? 3 : 2);
 
     // this slot's buffers may still be read by the side-stream reduction of its previous MSM
@@ -673,7 +671,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             size_t smem = 0;
             if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
             else if (g2) { kacc = g2_minb == 3 ? k_msm_accumulate<F, false, 3> : k_msm_accumulate<F, false, 2>; }
-            else { kacc = g1_minb == 4 ? k_msm_accumulate<F, false, 4> : k_msm_accumulate<F, false, 3>; }
+            else { kacc = k_msm_accumulate<F, false, 3>; }   // 128 registers: four CTAs (16 warps) per SM
             B200_LAUNCH(ctx, kacc, agrid, 128, smem, bs, d_entries, d_hist, d_tasks, d_plan + 2, g.CAP, d_hot_base, d_buckets, d_partial, add_existing);
         }
         phase_end(ctx);

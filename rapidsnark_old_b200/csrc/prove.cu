@@ -383,6 +383,7 @@ int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_ou
 // zkey sharded over several GPUs the caller exchanges the transformed polynomials between the stages (on the H
 // stream), each rank having run only the chains it owns.
 static int prove_stage1(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, unsigned poly_mask, bool combine) {
+    if (zk->stage1_done) { c->err = "prove_begin: the previous b200_prove_begin has not been finished"; return B200_ERR_ARG; }
     cudaSetDevice(c->device);
     phase_reset(c);
     B200_TRY(wtns_upload(c, zk, wtns, wtns_on_device));

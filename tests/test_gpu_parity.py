@@ -293,6 +293,10 @@ def test_two_stage_prove_equals_one_call(ctx, orc):
     assert orc.msms_to_affine(one) == orc.msms_to_affine(two) == synth_util.expected_affine(orc, s)
     with pytest.raises(b200.B200Error):
         zk.prove_finish()                      # no begin pending
+    zk.prove_begin(wt, False, 7)
+    with pytest.raises(b200.B200Error):
+        zk.prove_begin(wt, False, 7)           # a begin is pending
+    assert orc.msms_to_affine(zk.prove_finish()) == orc.msms_to_affine(one)
     zk.free()
 
 

@@ -30,7 +30,7 @@ def main():
     coefs = s.coefs_section()
     for cfg in args.configs:
         opts = dict(kv.split("=") for kv in cfg.split(",") if kv)
-        for k in ("precomp", "precomp_c", "acc_smem", "msm_window", "target_tasks_log2", "h_streams", "g1_minb", "g2_minb", "warm_max", "reduce_l", "reduce_l_g2", "tree_threads"):
+        for k in ("precomp", "precomp_c", "acc_smem", "msm_window", "target_tasks_log2", "h_streams", "g2_minb", "warm_max", "reduce_l", "reduce_l_g2", "tree_threads"):
             ctx.set_option(k, int(opts.get(k, -1 if k in ("precomp", "acc_smem") else 0)))
         shards = int(opts.get("shards", 1))     # this GPU plays rank 0 of `shards` (per-rank time of an N-GPU run)
         t0 = time.time()
