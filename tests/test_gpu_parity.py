@@ -337,6 +337,32 @@ def test_zkey_upload_rejects_bad_records(ctx):
         ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, bytes(bad), p["A"], p["B1"], p["B2"], p["C"], p["H"])
 
 
+@pytest.mark.parametrize("opts", [{"reduce_l": 16}, {"reduce_l": 4, "reduce_l_g2": 2}, {"tree_threads": 32},
+                                  {"tree_threads": 128, "warm_max": 2}, {"warm_max": 64}, {"h_streams": 3},
+                                  {"g2_minb": 3}, {"log_n": 12, "reduce_l": 8, "tree_threads": 32, "warm_max": 2}])
+def test_prove_msms_scheduling_options(ctx, orc, opts):
+    """Reduce-segment length, tree CTA size, fold threshold, transform streams, G2 occupancy variant: scheduling
+    knobs only - the five points never change.  A skewed witness makes the fold paths (warm / hot) do real work."""
+    opts = dict(opts)
+    s = synth_util.make(opts.pop("log_n", 10))    # 2^12: resident per-window tables, 2^10: plain multi-window path
+    wt = bytearray(s.wtns_bytes())
+    for i in range(8, s.n_vars, 3):               # two thirds of the wires become 0 / 1: huge |digit| = 1 buckets
+        wt[32 * i:32 * i + 32] = (i & 1).to_bytes(32, "little")
+    wt = bytes(wt)
+    p = s.points
+    coefs = s.coefs_section()
+    ref = orc.prove_msms(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"], wt)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        zk = _upload(ctx, s)
+        assert orc.msms_to_affine(zk.prove_msms(wt)) == orc.msms_to_affine(ref)
+        zk.free()
+    finally:
+        for k in opts:
+            ctx.set_option(k, 0)
+
+
 @pytest.mark.parametrize("precomp,pc", [(0, 0), (1, 12), (1, 16), (1, 20)])
 def test_prove_msms_table_variants(ctx, orc, precomp, pc):
     """resident per-window tables (any window width) and the plain multi-window path give the same points."""

@@ -25,7 +25,9 @@ def main():
     ap.add_argument("--g2", action="store_true")
     ap.add_argument("--c", type=int, default=0)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--scalars", default="full", choices=["full", "fr"])
+    ap.add_argument("--scalars", default="full", choices=["full", "fr", "circom"],
+                    help="full: uniform 256-bit; fr: uniform below r; circom: 70 %% of the scalars in {0,1}, 20 %% < 2^32, "
+                         "10 %% uniform below r (SURVEY.md 8d config 2, the shape of real circom witnesses)")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--acc-smem", type=int, default=-1)
     ap.add_argument("--cpu-max-log-n", type=int, default=0,
@@ -60,8 +62,16 @@ def main():
         if n > pool:
             d_bases = d_bases.repeat(n // pool)
         sc = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * 2 + 1
-        if args.scalars == "fr":
+        if args.scalars in ("fr", "circom"):
             sc[:, 3] &= (1 << 61) - 1
+        if args.scalars == "circom":
+            kind = rng.random(n)
+            small = kind < 0.7
+            mid = (kind >= 0.7) & (kind < 0.9)
+            sc[small] = 0
+            sc[small, 0] = rng.integers(0, 2, size=int(small.sum()), dtype=np.uint64)
+            sc[mid] = 0
+            sc[mid, 0] = rng.integers(0, 1 << 32, size=int(mid.sum()), dtype=np.uint64)
         d_sc = torch.from_numpy(sc.view(np.uint8).reshape(-1).copy()).cuda()
         run = ctx.msm_g2_dev if args.g2 else ctx.msm_g1_dev
         out = run(d_bases.data_ptr(), d_sc.data_ptr(), n)      # warm-up + optional check
