@@ -112,6 +112,12 @@ int b200_prove_begin(b200_ctx *ctx, b200_zkey *zk, const void *wtns, int wtns_on
                      void **d_abc3, void **h_stream);
 int b200_prove_finish(b200_ctx *ctx, b200_zkey *zk, void *out768);
 
+/* Exchange step for ONE process driving n GPUs (ctxs[g] / zks[g] = shard g, all after b200_prove_begin with
+ * poly_mask = the polynomials i with i % n == g): every transformed polynomial is copied from its owner into the
+ * other shards' buffers, device to device (cudaMemcpyPeerAsync over NVLink), ordered on the H streams - the
+ * in-process counterpart of the NCCL broadcasts of dist.py.  No host synchronisation. */
+int b200_exchange_polys(b200_ctx *const *ctxs, b200_zkey *const *zks, int n);
+
 /* ---- synthetic tables: k_i * G for known k_i (fixed-base, device side), affine Montgomery out ------ */
 int b200_fixed_base_g1(b200_ctx *ctx, const void *base_affine64, const void *scalars32, uint64_t n, void *out_affine);
 int b200_fixed_base_g2(b200_ctx *ctx, const void *base_affine128, const void *scalars32, uint64_t n, void *out_affine);

@@ -29,7 +29,7 @@ EXPORTS = [
     "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window", "b200_set_option",
     "b200_ntt_fr", "b200_ntt_fr_dev",
     "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
-    "b200_prove_begin", "b200_prove_finish",
+    "b200_prove_begin", "b200_prove_finish", "b200_exchange_polys",
     "b200_groth16_finalize", "b200_fq_to_decimal",
     "b200_fixed_base_g1", "b200_fixed_base_g2",
     "b200_host_fq_mul", "b200_host_fq_add", "b200_host_fq_sub", "b200_host_fq_neg", "b200_host_fq_inv",
@@ -85,6 +85,7 @@ def lib():
         L.b200_prove_msms_dev.argtypes = [_vp, _vp, _vp, _vp]
         L.b200_prove_begin.argtypes = [_vp, _vp, _vp, _int, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]
         L.b200_prove_finish.argtypes = [_vp, _vp, _vp]
+        L.b200_exchange_polys.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _int]
         L.b200_stream.restype = _vp
         L.b200_stream.argtypes = [_vp]
         L.b200_groth16_finalize.argtypes = [_vp] * 9
@@ -143,6 +144,17 @@ def proof_json(proof256):
     d = [fq_to_decimal(proof256[i * 32:(i + 1) * 32]) for i in range(8)]
     return ('{"pi_a":["%s","%s","1"],"pi_b":[["%s","%s"],["%s","%s"],["1","0"]],"pi_c":["%s","%s","1"],'
             '"protocol":"groth16"}' % (d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]))
+
+
+def exchange_polys(zkeys):
+    """In-process multi-GPU exchange (b200_exchange_polys): zkeys[g] = shard g of len(zkeys), each after
+    prove_begin(..., poly_mask = polynomials i with i % n == g)."""
+    n = len(zkeys)
+    ctxs = (_vp * n)(*[z.ctx.handle for z in zkeys])
+    zks = (_vp * n)(*[z.handle for z in zkeys])
+    rc = lib().b200_exchange_polys(ctxs, zks, n)
+    if rc != OK:
+        raise B200Error(rc, "b200_exchange_polys failed")
 
 
 def fold_partials(parts768):

@@ -35,6 +35,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t hstream = nullptr;    // H pipeline (a,b,c build + NTTs) overlapping the witness MSMs
     cudaEvent_t ev_h = nullptr;
+    unsigned long long peer_enabled = 0;   // devices this ctx's device has been given peer access to
     int hi_prio = 0;                   // stream priority of the side / H streams
     cudaStream_t hstream_bc[2] = {nullptr, nullptr};   // b and c transform chains beside a's (opt_h_streams = 3)
     cudaEvent_t ev_h_fork = nullptr, ev_h_join[2] = {nullptr, nullptr};

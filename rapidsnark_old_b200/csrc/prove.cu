@@ -462,6 +462,37 @@ int b200_prove_begin(b200_ctx *h, b200_zkey *zk, const void *wtns, int wtns_on_d
     return B200_OK;
 }
 
+int b200_exchange_polys(b200_ctx *const *hs, b200_zkey *const *zks, int n) {
+    if (!hs || !zks || n < 1) return B200_ERR_ARG;
+    for (int g = 0; g < n; g++)
+        if (!hs[g] || !zks[g] || !zks[g]->stage1_done || zks[g]->stage1_combined ||
+            zks[g]->domain_size != zks[0]->domain_size) {
+            if (hs[g]) hs[g]->c.err = "exchange_polys: every shard needs a pending b200_prove_begin of the same circuit";
+            return B200_ERR_ARG;
+        }
+    const size_t bytes = (size_t)zks[0]->domain_size * sizeof(Fr);
+    for (int i = 0; i < 3; i++) {
+        const int o = i % n;
+        Ctx *co = &hs[o]->c;
+        Fr *src = i == 0 ? zks[o]->d_a : i == 1 ? zks[o]->d_b : zks[o]->d_c;
+        for (int r = 0; r < n; r++) {
+            if (r == o) continue;
+            Ctx *cr = &hs[r]->c;
+            Fr *dst = i == 0 ? zks[r]->d_a : i == 1 ? zks[r]->d_b : zks[r]->d_c;
+            cudaSetDevice(cr->device);
+            if (cr->device != co->device && !(cr->peer_enabled & (1ull << co->device)) && co->device < 64) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(co->device, 0);   // direct NVLink path when available
+                if (e != cudaSuccess) cudaGetLastError();                    // already enabled / unsupported: staged copy
+                cr->peer_enabled |= 1ull << co->device;
+            }
+            // co->ev_h: recorded on the owner's H stream behind its transform chains (h_on_device)
+            B200_CUDA_CHECK(cr, cudaStreamWaitEvent(cr->hstream, co->ev_h, 0));
+            B200_CUDA_CHECK(cr, cudaMemcpyPeerAsync(dst, cr->device, src, co->device, bytes, cr->hstream));
+        }
+    }
+    return B200_OK;
+}
+
 int b200_prove_finish(b200_ctx *h, b200_zkey *zk, void *out768) {
     if (!h || !zk || !out768) return B200_ERR_ARG;
     return prove_stage2(&h->c, zk, out768);

@@ -4,6 +4,8 @@
 #include <sys/random.h>
 #include <sstream>
 #include <stdexcept>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include "../../include/b200snark.h"
 
@@ -63,9 +65,11 @@ Prover<Engine>::Prover(uint32_t _nVars, uint32_t _nPublic, uint32_t _domainSize,
     int nGpus = 1, first = 0;
     if (const char *e = getenv("B200_GPUS")) nGpus = atoi(e) > 0 ? atoi(e) : 1;
     if (const char *e = getenv("B200_DEVICE")) first = atoi(e);
+    int stride = 1;    // B200_DEVICE_STRIDE=0: all shards on one device (exercises the N-GPU host path on a 1-GPU box)
+    if (const char *e = getenv("B200_DEVICE_STRIDE")) stride = atoi(e);
     for (int g = 0; g < nGpus; g++) {
         Gpu gp{nullptr, nullptr};
-        if (b200_init(first + g, &gp.ctx) != B200_OK) {
+        if (b200_init(first + g * stride, &gp.ctx) != B200_OK) {
             std::string msg = std::string("b200_init: ") + b200_last_error(nullptr);
             for (auto &o : gpus) { b200_zkey_free(o.zk); b200_free(o.ctx); }
             gpus.clear();
@@ -112,10 +116,51 @@ std::unique_ptr<Proof<Engine>> Prover<Engine>::prove(typename Engine::FrElement 
     std::vector<int> rcs(G, 0);
     if (G == 1) {
         rcs[0] = b200_prove_msms(gpus[0].ctx, gpus[0].zk, wtns, parts.data());
-    } else {
+    } else if (getenv("B200_REPLICATE_H")) {     // every GPU repeats the whole H pipeline (A/B, no exchange)
         std::vector<std::thread> th;
         for (size_t g = 0; g < G; g++)
             th.emplace_back([&, g]() { rcs[g] = b200_prove_msms(gpus[g].ctx, gpus[g].zk, wtns, parts.data() + 768 * g); });
+        for (auto &t : th) t.join();
+    } else {
+        // One host thread per GPU.  Stage 1 on every GPU (witness upload, its four witness MSMs, the transform
+        // chains of the polynomials it owns: polynomial i on GPU i % G), then ONE thread orders the device-to-device
+        // copies of the three transformed polynomials on the H streams, then stage 2 (combine, H MSM, collection).
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t arrived = 0;
+        int exchange_rc = -1;                     // -1: not done yet
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; g++)
+            th.emplace_back([&, g]() {
+                uint32_t mask = 0;
+                for (unsigned i = 0; i < 3; i++) if (i % G == g) mask |= 1u << i;
+                void *bufs[3], *hs = nullptr;
+                rcs[g] = b200_prove_begin(gpus[g].ctx, gpus[g].zk, wtns, 0, mask, bufs, &hs);
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    if (++arrived == G) {           // last one in: every stage 1 is enqueued
+                        bool all_ok = true;
+                        for (size_t k = 0; k < G; k++) all_ok = all_ok && rcs[k] == B200_OK;
+                        if (all_ok) {
+                            std::vector<b200_ctx *> cs(G);
+                            std::vector<b200_zkey *> zs(G);
+                            for (size_t k = 0; k < G; k++) { cs[k] = gpus[k].ctx; zs[k] = gpus[k].zk; }
+                            exchange_rc = b200_exchange_polys(cs.data(), zs.data(), (int)G);
+                        } else {
+                            exchange_rc = B200_ERR_ARG;
+                        }
+                        cv.notify_all();
+                    } else {
+                        cv.wait(lk, [&] { return exchange_rc != -1; });
+                    }
+                }
+                // a shard whose stage 1 went through is always finished (its streams and slots are drained), even
+                // when another shard or the exchange failed - the error is reported below
+                if (rcs[g] == B200_OK) {
+                    int rc = b200_prove_finish(gpus[g].ctx, gpus[g].zk, parts.data() + 768 * g);
+                    rcs[g] = rc != B200_OK ? rc : (exchange_rc == B200_OK ? B200_OK : exchange_rc);
+                }
+            });
         for (auto &t : th) t.join();
     }
     for (size_t g = 0; g < G; g++)

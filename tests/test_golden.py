@@ -192,10 +192,14 @@ def test_gpu_prove_matches_golden(gctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gpus", ["1", "2"])
+@pytest.mark.parametrize("gpus", ["1", "2", "3", "2-replicated"])
 def test_cli_output_is_byte_identical_to_reference_cli(tmp_path, gpus):
     """build/prover <zkey> <wtns> <proof.json> <public.json> vs the reference CLI's files for the same r, s.
-    B200_GPUS=2 runs two point-range shards (on one physical GPU if only one is present: B200_DEVICE stride 0)."""
+    B200_GPUS=N runs N point-range shards from one process: stage 1 per GPU, device-to-device exchange of the
+    transformed polynomials (b200_exchange_polys), stage 2 - on one physical GPU if fewer are present
+    (B200_DEVICE_STRIDE=0)."""
+    replicate = gpus.endswith("-replicated")
+    gpus = gpus.split("-")[0]
     zk, wt = tmp_path / "c.zkey", tmp_path / "w.wtns"
     zk.write_bytes(bytes.fromhex(C["zkey"]))
     wt.write_bytes(bytes.fromhex(C["wtns"]))
@@ -203,8 +207,10 @@ def test_cli_output_is_byte_identical_to_reference_cli(tmp_path, gpus):
     if gpus != "1":
         import torch
         if torch.cuda.device_count() < int(gpus):
-            pytest.skip("needs %s GPUs" % gpus)
+            env["B200_DEVICE_STRIDE"] = "0"
         env["B200_GPUS"] = gpus
+        if replicate:
+            env["B200_REPLICATE_H"] = "1"
     r = subprocess.run([PROVER, str(zk), str(wt), str(tmp_path / "proof.json"), str(tmp_path / "public.json")],
                        capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr

@@ -328,6 +328,27 @@ def test_h_pipeline_spread_over_ranks(orc, shards):
         c.close()
 
 
+@pytest.mark.parametrize("shards", [2, 4])
+def test_in_process_exchange(orc, shards):
+    """b200_exchange_polys: the exchange step of ONE process driving N GPUs (the C++ host prover with B200_GPUS=N),
+    here N contexts on one device.  Also: the call is refused unless every shard has a begin pending."""
+    from rapidsnark_old_b200 import dist as bdist
+    s = synth_util.make(10)
+    wt = s.wtns_bytes()
+    ctxs = [b200.Context(0) for _ in range(shards)]
+    zks = [_upload(c, s, i, shards) for i, c in enumerate(ctxs)]
+    with pytest.raises(b200.B200Error):
+        b200.exchange_polys(zks)
+    for i, zk in enumerate(zks):
+        zk.prove_begin(wt, False, bdist.poly_mask(i, shards))
+    b200.exchange_polys(zks)
+    parts = [zk.prove_finish() for zk in zks]
+    assert orc.msms_to_affine(b200.fold_partials(parts)) == synth_util.expected_affine(orc, s)
+    for zk, c in zip(zks, ctxs):
+        zk.free()
+        c.close()
+
+
 def test_zkey_upload_rejects_bad_records(ctx):
     s = synth_util.make(4)
     p = s.points
