@@ -79,12 +79,14 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     g.nbk = 1u << (c - 1);
     g.nwin_b = shared_buckets ? 1u : (u32)g.nwin;
     g.NB = g.nwin_b * g.nbk;
-    // task cap: with plenty of buckets (>= 2^18) a task is a whole bucket unless it is 4x the average;
+    // task cap: with plenty of buckets (>= 2^18) a task is a whole bucket unless it is 2x the average (uniform digits
+    // never get there - the bucket sizes are Poisson around the average - while the huge |digit| = 1 buckets of a
+    // circom-style witness are cut into pieces short enough not to be the kernel's long pole);
     // with few, large buckets they are cut so that about MSM_TARGET_TASKS tasks exist (load balance)
     uint64_t ent = n_batch * (uint64_t)g.nwin;
     uint64_t avg = ent / g.NB + 1;
     u32 cap = 32;
-    if ((ent < g.NB ? ent : g.NB) >= (1u << 18)) { while (cap < 4 * avg && cap < MSM_MAX_CAP) cap <<= 1; }
+    if ((ent < g.NB ? ent : g.NB) >= (1u << 18)) { while (cap < 2 * avg && cap < MSM_MAX_CAP) cap <<= 1; }
     else { while ((uint64_t)cap * 2 * target_tasks <= ent && cap < MSM_MAX_CAP) cap <<= 1; }
     g.CAP = cap;
     // reduce segments: longer for big bucket sets (amortises the per-segment multiplier, keeps the side-stream

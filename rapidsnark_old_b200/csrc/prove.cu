@@ -329,10 +329,14 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
 // witness upload, then a,b,c -> h.  With `overlap` the H pipeline runs on its own stream (c->hstream) so that
 // the witness MSMs, which do not depend on it, can start right after the upload; the caller makes the H MSM
 // wait on c->ev_h.
-static int wtns_upload(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device) {
+// `slice_only`: a shard that builds none of a, b, c (it receives them) only reads its own range of the witness
+static int wtns_upload(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, bool slice_only = false) {
+    const size_t lo = slice_only ? (size_t)zk->rA.lo * 32 : 0;
+    const size_t hi = slice_only ? (size_t)zk->rA.hi * 32 : (size_t)zk->n_vars * 32;
     phase_begin(c, PH_H2D);
-    B200_CUDA_CHECK(c, cudaMemcpyAsync(zk->d_wtns, wtns, (size_t)zk->n_vars * 32,
-                                        wtns_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (hi > lo)
+        B200_CUDA_CHECK(c, cudaMemcpyAsync((uint8_t *)zk->d_wtns + lo, (const uint8_t *)wtns + lo, hi - lo,
+                                            wtns_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     phase_end(c);
     return B200_OK;
 }
@@ -386,7 +390,7 @@ static int prove_stage1(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_de
     if (zk->stage1_done) { c->err = "prove_begin: the previous b200_prove_begin has not been finished"; return B200_ERR_ARG; }
     cudaSetDevice(c->device);
     phase_reset(c);
-    B200_TRY(wtns_upload(c, zk, wtns, wtns_on_device));
+    B200_TRY(wtns_upload(c, zk, wtns, wtns_on_device, poly_mask == 0 && !combine));
     B200_CUDA_CHECK(c, cudaEventRecord(c->ev_h, c->stream));   // "witness uploaded"
     const uint8_t *w = (const uint8_t *)zk->d_wtns;
     // groth16.cpp:173 / :183 / :190 / :197 / :204, restricted to this shard's point range.  All five MSMs are
