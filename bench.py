@@ -84,10 +84,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def build_inputs(log_n, seed, g1_many, g2_many):
+def build_inputs(log_n, seed, g1_many, g2_many, fast=True):
+    """The synthetic circuit of SURVEY.md Appendix C.  fast: scalars from the library's host routine (FastSynth,
+    identical values, seconds instead of minutes at 2^24); the point makers must then accept packed bytes."""
     from rapidsnark_old_b200 import synth
     t = time.time()
-    s = synth.Synth(log_n, seed)
+    s = synth.FastSynth(log_n, seed) if fast else synth.Synth(log_n, seed)
     log("[bench] synthetic circuit 2^%d: scalars in %.1fs" % (log_n, time.time() - t))
     t = time.time()
     s.build_points(g1_many, g2_many)
@@ -98,8 +100,8 @@ def build_inputs(log_n, seed, g1_many, g2_many):
 def gpu_point_makers(ctx):
     from rapidsnark_old_b200 import synth
     g1, g2 = synth.g1_gen_bytes(), synth.g2_gen_bytes()
-    return (lambda ks: ctx.fixed_base_g1(g1, synth.le32_many(ks), len(ks)),
-            lambda ks: ctx.fixed_base_g2(g2, synth.le32_many(ks), len(ks)))
+    return (lambda ks: ctx.fixed_base_g1(g1, synth.le32_many(ks), synth.count32(ks)),
+            lambda ks: ctx.fixed_base_g2(g2, synth.le32_many(ks), synth.count32(ks)))
 
 
 def peaks():
@@ -129,7 +131,7 @@ def run_reference(args):
         import synth_util
         ctx, makers = None, synth_util.oracle_point_makers(o)
     log_n = args.log_n
-    s = build_inputs(log_n, 2, *makers)
+    s = build_inputs(log_n, 2, *makers, fast=ctx is not None)
     if ctx:
         ctx.close()
     p, vk = s.points, s.vk
@@ -324,9 +326,7 @@ def check_known_dlogs(b200, s, msms, proof, r32, s32):
     multiples of the generators and must satisfy the Groth16 equation."""
     from rapidsnark_old_b200 import synth
     R = synth.R
-    w, V, P = s.wtns, s.n_vars, s.n_public
-    ea = sum(w[i] * s.A_tau[i] for i in range(V)) % R
-    eb = sum(w[i] * s.B_tau[i] for i in range(V)) % R
+    ea, eb = s.dlog_a, s.dlog_b
     r, t = int.from_bytes(r32, "little"), int.from_bytes(s32, "little")
     a = (s.alpha + ea + r * s.delta) % R
     b = (s.beta + eb + t * s.delta) % R
@@ -336,8 +336,7 @@ def check_known_dlogs(b200, s, msms, proof, r32, s32):
     assert proof[:64] == A, "proof.A does not match its known discrete log"
     assert proof[64:192] == B, "proof.B does not match its known discrete log"
     # C: solve the verification equation for c and compare: a*b = alpha*beta + pub + c*delta
-    pub = sum(w[i] * s.K[i] for i in range(P + 1)) % R
-    c = (a * b - s.alpha * s.beta - pub) * pow(s.delta, -1, R) % R
+    c = (a * b - s.alpha * s.beta - s.dlog_pub) * pow(s.delta, -1, R) % R
     C = b200.host_g1_to_affine(b200.host_g1_mul(g1, c.to_bytes(32, "little")))
     assert proof[192:256] == C, "proof.C does not satisfy the Groth16 verification equation"
     log("[bench] proof verified in the exponent (A, B, C match; e(A,B) = e(alpha,beta) e(pub,gamma) e(C,delta))")

@@ -122,6 +122,16 @@ int b200_exchange_polys(b200_ctx *const *ctxs, b200_zkey *const *zks, int n);
 int b200_fixed_base_g1(b200_ctx *ctx, const void *base_affine64, const void *scalars32, uint64_t n, void *out_affine);
 int b200_fixed_base_g2(b200_ctx *ctx, const void *base_affine128, const void *scalars32, uint64_t n, void *out_affine);
 
+/* Scalars of the synthetic chain circuit used by bench.py and the tests (the same values as
+ * rapidsnark_old_b200/synth.py, computed on the host in C++): inputs are 32-byte little-endian integers below r
+ * (toxic waste tau, alpha, beta, gamma, delta and the free wire w_1), outputs normal-form 32-byte integers:
+ * wtns[V], a_tau[V], b_tau[V] (A_s(tau), B_s(tau)), c_scalars[V - P - 1], ic_scalars[P + 1], h_tbl[n] (the known
+ * discrete logs of the five point tables), dlogs96 = sum w_s A_s | sum w_s B_s | sum_{s <= P} w_s K_s.
+ * V = 2^log_n - 6, P = n_public.  CPU only (no ctx). */
+int b200_synth_chain(uint32_t log_n, uint32_t n_public, const void *tau32, const void *alpha32, const void *beta32,
+                     const void *gamma32, const void *delta32, const void *w1_32, void *wtns, void *a_tau, void *b_tau,
+                     void *c_scalars, void *ic_scalars, void *h_tbl, void *dlogs96);
+
 /* ---- host-side group/field helpers (same arithmetic templates as the kernels, compiled for the CPU;
  *      used for the O(1) blinding work of groth16.cpp:209-253 and to fold gathered partial results) --- */
 void b200_host_fq_mul(void *r, const void *a, const void *b);

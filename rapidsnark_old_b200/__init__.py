@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
     "b200_prove_begin", "b200_prove_finish", "b200_exchange_polys",
     "b200_groth16_finalize", "b200_fq_to_decimal",
-    "b200_fixed_base_g1", "b200_fixed_base_g2",
+    "b200_fixed_base_g1", "b200_fixed_base_g2", "b200_synth_chain",
     "b200_host_fq_mul", "b200_host_fq_add", "b200_host_fq_sub", "b200_host_fq_neg", "b200_host_fq_inv",
     "b200_host_fr_mul", "b200_host_fr_add", "b200_host_fr_sub", "b200_host_fr_neg", "b200_host_fr_inv",
     "b200_host_fq2_mul", "b200_host_fq2_sqr",
@@ -92,6 +92,7 @@ def lib():
         L.b200_fq_to_decimal.argtypes = [_vp, _vp]
         L.b200_fixed_base_g1.argtypes = [_vp, _vp, _vp, _u64, _vp]
         L.b200_fixed_base_g2.argtypes = [_vp, _vp, _vp, _u64, _vp]
+        L.b200_synth_chain.argtypes = [_u32, _u32] + [_vp] * 13
         L.b200_last_phase_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), _int]
         _lib = L
     return _lib

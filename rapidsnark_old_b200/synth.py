@@ -59,7 +59,14 @@ def batch_inverse(vals):
 
 
 def le32_many(vals):
+    if isinstance(vals, (bytes, bytearray, memoryview)):      # already packed (FastSynth)
+        return bytes(vals)
     return b"".join(int(v).to_bytes(32, "little") for v in vals)
+
+
+def count32(vals):
+    """Number of 32-byte scalars in a list of integers or a packed byte string."""
+    return len(vals) // 32 if isinstance(vals, (bytes, bytearray, memoryview)) else len(vals)
 
 
 class Synth:
@@ -172,6 +179,19 @@ class Synth:
         assert len(self.points["A"]) == 64 * V and len(self.points["C"]) == 64 * (V - P - 1)
         return self
 
+    # known discrete logs used by the in-the-exponent proof check of bench.py
+    @property
+    def dlog_a(self):
+        return sum(w * a for w, a in zip(self.wtns, self.A_tau)) % R
+
+    @property
+    def dlog_b(self):
+        return sum(w * b for w, b in zip(self.wtns, self.B_tau)) % R
+
+    @property
+    def dlog_pub(self):
+        return sum(self.wtns[i] * self.K[i] for i in range(self.n_public + 1)) % R
+
     # ---- expected discrete logs of the five pre-blinding MSM results (groth16.cpp:165-207)
     def expected_dlogs(self, h_scalars=None):
         w, V, P = self.wtns, self.n_vars, self.n_public
@@ -212,6 +232,67 @@ class Synth:
             k = (-2) * ninv % R
             out.append(((fa * k) * (fb * k) - fc * k) % R)
         return out
+
+
+class FastSynth:
+    """The same circuit instance as Synth(log_n, seed, n_public) with the big vectors computed by the library's
+    host routine b200_synth_chain (C++, seconds at 2^24 instead of minutes) and kept as packed little-endian bytes
+    instead of lists of Python integers.  Interface used by bench.py / tools: n, n_vars, n_public, n_coefs, toxic
+    waste, wtns_bytes(), coefs_section(), build_points(), points, vk, dlog_a / dlog_b / dlog_pub."""
+
+    def __init__(self, log_n, seed=1, n_public=4):
+        import ctypes
+        from . import lib
+        rnd = random.Random(seed)
+        n = 1 << log_n
+        assert n >= 16
+        self.log_n, self.n, self.n_public = log_n, n, n_public
+        V = self.n_vars = n - 6
+        P = n_public
+        self.n_cons = V - 2
+        self.tau, self.alpha, self.beta, self.gamma, self.delta = (rnd.randrange(2, R) for _ in range(5))
+        w1 = rnd.randrange(2, R)
+        self.n_coefs = 3 * self.n_cons + P + 1
+        b = lambda v: int(v).to_bytes(32, "little")
+        mk = lambda k: ctypes.create_string_buffer(32 * k)
+        wt, a, bb, cs, ic, h, dl = mk(V), mk(V), mk(V), mk(V - P - 1), mk(P + 1), mk(n), mk(3)
+        rc = lib().b200_synth_chain(log_n, P, b(self.tau), b(self.alpha), b(self.beta), b(self.gamma), b(self.delta),
+                                    b(w1), wt, a, bb, cs, ic, h, dl)
+        if rc != 0:
+            raise ValueError("b200_synth_chain failed (%d)" % rc)
+        self._wtns = wt.raw
+        self.A_tau, self.B_tau, self.c_scalars, self.ic_scalars, self.h_scalars_tbl = a.raw, bb.raw, cs.raw, ic.raw, h.raw
+        self.dlog_a, self.dlog_b, self.dlog_pub = (int.from_bytes(dl.raw[32 * i:32 * i + 32], "little") for i in range(3))
+        self.points = None
+
+    def wtns_bytes(self):
+        return self._wtns
+
+    def coefs_section(self):
+        import numpy as np
+        nc, P = self.n_cons, self.n_public
+        rec = np.dtype([("m", "<u4"), ("c", "<u4"), ("s", "<u4"), ("v", "V32")])
+        out = np.zeros(self.n_coefs, dtype=rec)
+        r2 = MONT * MONT % R
+        one, three = (np.frombuffer((v * r2 % R).to_bytes(32, "little"), dtype="V32")[0] for v in (1, 3))
+        j = np.arange(nc, dtype=np.uint32)
+        body = out[:3 * nc].reshape(nc, 3)
+        body["c"] = j[:, None]
+        body["m"][:, 2] = 1
+        body["s"][:, 0] = j
+        body["s"][:, 1] = j + 1
+        body["s"][:, 2] = j + 1
+        body["v"][:, 0] = one
+        body["v"][:, 1] = three
+        body["v"][:, 2] = one
+        tail = out[3 * nc:]
+        i = np.arange(P + 1, dtype=np.uint32)
+        tail["c"] = nc + i
+        tail["s"] = i
+        tail["v"] = one
+        return struct.pack("<I", self.n_coefs) + out.tobytes()
+
+    build_points = Synth.build_points
 
 
 # ----------------------------------------------------------------------------- iden3 binfile writers

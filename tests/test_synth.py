@@ -43,3 +43,44 @@ def test_binfile_layout_roundtrip(tmp_path):
     assert z[:4] == b"zkey" and int.from_bytes(z[8:12], "little") == 10
     w = synth.wtns_bytes_file(s)
     assert w[:4] == b"wtns"
+
+
+@pytest.mark.parametrize("log_n,n_public", [(4, 4), (5, 1), (8, 4), (11, 7)])
+def test_fast_synth_equals_python_synth(log_n, n_public):
+    """b200_synth_chain (C++ host routine behind synth.FastSynth, what bench.py uses) produces the same witness,
+    table scalars, coefficient section and known discrete logs as the Python big-integer generator."""
+    a, b = synth.Synth(log_n, 3, n_public), synth.FastSynth(log_n, 3, n_public)
+    assert (a.tau, a.alpha, a.beta, a.gamma, a.delta) == (b.tau, b.alpha, b.beta, b.gamma, b.delta)
+    assert a.wtns_bytes() == b.wtns_bytes()
+    assert synth.le32_many(a.A_tau) == b.A_tau and synth.le32_many(a.B_tau) == b.B_tau
+    assert synth.le32_many(a.c_scalars) == b.c_scalars and synth.le32_many(a.ic_scalars) == b.ic_scalars
+    assert synth.le32_many(a.h_scalars_tbl) == b.h_scalars_tbl
+    assert a.coefs_section() == b.coefs_section() and a.n_coefs == b.n_coefs
+    assert (a.dlog_a, a.dlog_b, a.dlog_pub) == (b.dlog_a, b.dlog_b, b.dlog_pub)
+    assert synth.count32(b.A_tau) == a.n_vars == synth.count32(a.A_tau)
+
+
+def test_bench_inputs_and_exponent_check_on_cpu():
+    """bench.py's input builder (FastSynth + point makers fed packed bytes) and its in-the-exponent proof check,
+    end to end on the CPU: the oracle plays the prover."""
+    import os
+    import sys
+    sys.path.insert(0, oracle_lib.ROOT)
+    import bench
+    import rapidsnark_old_b200 as b200
+    o = oracle_lib.best()
+    g1m, g2m = synth_util.oracle_point_makers(o)
+    unpack = lambda ks: [int.from_bytes(ks[i:i + 32], "little") for i in range(0, len(ks), 32)] \
+        if isinstance(ks, (bytes, bytearray)) else ks
+    s = bench.build_inputs(6, 2, lambda ks: g1m(unpack(ks)), lambda ks: g2m(unpack(ks)))
+    assert isinstance(s, synth.FastSynth)
+    p, vk = s.points, s.vk
+    msms = o.prove_msms(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"],
+                        p["H"], s.wtns_bytes())
+    r32, s32 = (12345).to_bytes(32, "little"), (67890).to_bytes(32, "little")
+    proof = b200.groth16_finalize(msms, vk, r32, s32)
+    bench.check_known_dlogs(b200, s, msms, proof, r32, s32)
+    bad = bytearray(proof)
+    bad[200] ^= 1
+    with pytest.raises(AssertionError):
+        bench.check_known_dlogs(b200, s, msms, bytes(bad), r32, s32)
