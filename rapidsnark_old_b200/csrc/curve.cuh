@@ -120,6 +120,39 @@ HD void ec_madd_acc(Acc &acc, const Affine<F> &q) {
     acc.st_y(hmul_sub_mul(r, fsub(qq, x3), y1, ppp));
 }
 
+// Same addition with the affine operand behind an accessor too (ld_x / ld_y / is_zero / get): the experimental
+// accumulation variant of msm.cuh stages the gathered points in shared memory and loads each coordinate where it is
+// used, so neither the running sum nor the (current, prefetched) points occupy registers across the products.
+template <class Acc, class Pt>
+HD void ec_madd_acc_pt(Acc &acc, Pt &q) {
+    typedef typename Pt::Field F;
+    if (q.is_zero()) return;
+    F zz = acc.ld_zz();
+    if (zz.is_zero()) {
+        acc.st_x(q.ld_x()); acc.st_y(q.ld_y()); acc.st_zz(F::one()); acc.st_zzz(F::one());
+        return;
+    }
+    F p = fsub(hmul(q.ld_x(), zz), acc.ld_x());
+    {
+        F r = fsub(hmul(q.ld_y(), acc.ld_zzz()), acc.ld_y());
+        if (p.is_zero()) {
+            if (r.is_zero()) acc.st_all(ec_dbl_affine(q.get()));   // same point
+            else acc.st_all(Xyzz<F>::zero());                       // opposite points
+            return;
+        }
+        q.st_scratch(0, r);              // the point's own slot is dead from here on: park r (needed last) in it
+    }
+    F pp = hsqr(p);
+    F ppp = hmul(p, pp);
+    q.st_scratch(1, ppp);
+    acc.st_zz(hmul(acc.ld_zz(), pp));
+    acc.st_zzz(hmul(acc.ld_zzz(), ppp));
+    F qq = hmul(acc.ld_x(), pp);
+    F x3 = fsub(fsub(hsqr(q.ld_scratch(0)), q.ld_scratch(1)), fdbl(qq));
+    acc.st_x(x3);
+    acc.st_y(hmul_sub_mul(q.ld_scratch(0), fsub(qq, x3), acc.ld_y(), q.ld_scratch(1)));
+}
+
 template <class F>
 HD void ec_madd(Xyzz<F> &acc, const Affine<F> &q) {
     RegAcc<F> a;

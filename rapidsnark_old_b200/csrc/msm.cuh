@@ -313,6 +313,109 @@ struct SmemAcc {
     DEVFN Xyzz<F> get() const { Xyzz<F> r; r.x = ld(0); r.y = ld(1); r.zz = ld(2); r.zzz = ld(3); return r; }
 };
 
+// ---- experimental variant (option "acc_smem" = 2, G2 only, NOT the default; to be measured) -----------------------
+// The G2 loop keeps 250 registers alive (running sum 64, current + prefetched point 64, temporaries) and therefore
+// runs 8 warps per SM; ncu shows its warps mostly in fixed-latency `wait` with the multiplier pipe 67-73 % busy
+// (the G1 loop: 16 warps, 90 %).  Here the running sum AND the gathered points live in shared memory: the next
+// point is fetched with cp.async straight into a double-buffered slot (no registers, no stall), coordinates are
+// loaded where they are used.  512 bytes of shared memory per thread (64 KB per CTA, 3 CTAs per SM).
+DEVFN void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+DEVFN void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DEVFN void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <class F>
+struct SmemPoint {            // one affine point of this thread in shared memory: unit k at base[k * blockDim.x]
+    typedef F Field;
+    uint4 *base;              // already offset by threadIdx.x
+    bool neg;                 // the entry's sign bit: use -y
+    static const int FV = sizeof(F) / 16;
+    DEVFN F ld(int field) const {
+        F r;
+        uint4 *d = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+        for (int i = 0; i < FV; i++) d[i] = base[(field * FV + i) * blockDim.x];
+        return r;
+    }
+    DEVFN F ld_x() const { return ld(0); }
+    DEVFN F ld_y() const { F y = ld(1); return neg ? fneg(y) : y; }
+    DEVFN bool is_zero() const {
+        uint4 t = base[0];
+#pragma unroll
+        for (int i = 1; i < 2 * FV; i++) { uint4 u = base[i * blockDim.x]; t.x |= u.x; t.y |= u.y; t.z |= u.z; t.w |= u.w; }
+        return (t.x | t.y | t.z | t.w) == 0;
+    }
+    DEVFN Affine<F> get() const { Affine<F> a; a.x = ld_x(); a.y = ld_y(); return a; }
+    // once both coordinates have been consumed the slot is free: scratch element 0 / 1 of the running addition
+    DEVFN void st_scratch(int field, const F &v) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(&v);
+#pragma unroll
+        for (int i = 0; i < FV; i++) base[(field * FV + i) * blockDim.x] = s[i];
+    }
+    DEVFN F ld_scratch(int field) const { return ld(field); }
+};
+
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate_staged(const Affine<F> *__restrict__ bases,
+                                                                       const u32 *__restrict__ entries,
+                                                                       const u32 *__restrict__ off,
+                                                                       const uint2 *__restrict__ tasks,
+                                                                       const u32 *__restrict__ ntasks_ptr, u32 CAP,
+                                                                       const u32 *__restrict__ hot_base,
+                                                                       Xyzz<F> *__restrict__ buckets,
+                                                                       Xyzz<F> *__restrict__ partial, int add_existing) {
+    extern __shared__ uint4 smem_raw[];
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *ntasks_ptr) return;
+    const uint2 task = tasks[t];
+    const u32 b = task.x;
+    const u32 o0 = off[b], cnt = off[b + 1] - o0;
+    const u32 start = o0 + task.y * CAP;
+    const u32 len = (cnt - task.y * CAP < CAP) ? cnt - task.y * CAP : CAP;
+    constexpr int FV = sizeof(F) / 16;        // 16-byte units per field element
+    constexpr int PU = 2 * FV;                // units per affine point
+
+    SmemAcc<F> acc;
+    acc.base = smem_raw + threadIdx.x;                                   // units [0, 4 FV) x blockDim
+    uint4 *pt = smem_raw + (size_t)4 * FV * blockDim.x + threadIdx.x;    // two point buffers of PU units each
+    acc.st_all(Xyzz<F>::zero());
+
+    u32 e_next = entries[start];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bases + (e_next & 0x7fffffffu));
+#pragma unroll
+        for (int k = 0; k < PU; k++) cp_async16(pt + (size_t)k * blockDim.x, src + k);
+        cp_async_commit();
+    }
+    int buf = 0;
+    for (u32 k = 0; k < len; k++) {
+        const u32 e = e_next;
+        cp_async_wait_all();                                             // the point of entry k is in buffer `buf`
+        if (k + 1 < len) {
+            e_next = entries[start + k + 1];
+            const uint4 *src = reinterpret_cast<const uint4 *>(bases + (e_next & 0x7fffffffu));
+            uint4 *dst = pt + (size_t)(buf ^ 1) * PU * blockDim.x;
+#pragma unroll
+            for (int u = 0; u < PU; u++) cp_async16(dst + (size_t)u * blockDim.x, src + u);
+            cp_async_commit();
+        }
+        SmemPoint<F> q;
+        q.base = pt + (size_t)buf * PU * blockDim.x;
+        q.neg = (e >> 31) != 0;
+        ec_madd_acc_pt(acc, q);
+        buf ^= 1;
+    }
+    Xyzz<F> r = acc.get();
+    if (cnt <= CAP) {
+        if (add_existing) { Xyzz<F> old = ld_struct(buckets + b); ec_add(r, old); }
+        st_struct(buckets + b, r);
+    } else {
+        st_struct(partial + hot_base[b] + task.y, r);
+    }
+}
+
 template <class F, bool ACC_SMEM, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F> *__restrict__ bases,
                                                                 const u32 *__restrict__ entries,
@@ -671,7 +774,15 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             // variants: running sum in registers (default) or in shared memory
             void (*kacc)(const Affine<F> *, const u32 *, const u32 *, const uint2 *, const u32 *, u32, const u32 *, Pt *, Pt *, int);
             size_t smem = 0;
-            if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
+            if (ctx->opt_acc_smem == 2 && g2) {   // experimental: running sum + points staged in shared memory
+                kacc = k_msm_accumulate_staged<F, 3>;
+                smem = (size_t)128 * (sizeof(Pt) + 2 * sizeof(Affine<F>));
+                static bool attr_set = false;
+                if (!attr_set) {
+                    B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kacc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    attr_set = true;
+                }
+            } else if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
             else if (g2) { kacc = g2_minb == 3 ? k_msm_accumulate<F, false, 3> : k_msm_accumulate<F, false, 2>; }
             else { kacc = k_msm_accumulate<F, false, 3>; }   // 128 registers: four CTAs (16 warps) per SM
             B200_LAUNCH(ctx, kacc, agrid, 128, smem, bs, d_entries, d_hist, d_tasks, d_plan + 2, g.CAP, d_hot_base, d_buckets, d_partial, add_existing);

@@ -419,6 +419,22 @@ def test_msm_accumulator_variants(ctx, orc, acc_smem, g2):
     assert got == ref
 
 
+@pytest.mark.skipif(not os.environ.get("B200_EXPERIMENTAL"), reason="experimental kernel variant, not measured yet "
+                    "(set B200_EXPERIMENTAL=1): G2 accumulation with running sum and points staged in shared memory")
+@pytest.mark.parametrize("kind", ["full", "skew"])
+def test_msm_g2_staged_accumulation_variant(ctx, orc, kind):
+    """option acc_smem = 2 (msm.cuh k_msm_accumulate_staged): cp.async double-buffered points, 168 registers.  The
+    addition formula itself (ec_madd_acc_pt) is checked bit-for-bit on the CPU by tests/test_host_cpu.py."""
+    n = 4000
+    ctx.set_option("acc_smem", 2)
+    try:
+        bases, scalars = _g2_points(orc, 400, 31) * 10, _scalars(n, 32, kind)
+        got = orc.g2_to_affine(ctx.msm_g2(bases, scalars, n))
+    finally:
+        ctx.set_option("acc_smem", -1)
+    assert got == orc.g2_to_affine(orc.g2_msm(bases, scalars, n))
+
+
 def test_msm_hot_bucket_split(ctx, orc):
     """one bucket far larger than the task cap: sub-tasks + CTA merge (all scalars equal)."""
     n = 20000

@@ -58,7 +58,55 @@ int run2(long iters) {
     printf("Fq2: bad=%ld\n", bad);
     return bad != 0;
 }
+// ec_madd_acc_pt (the accessor form used by the experimental shared-memory-staged accumulation kernel, which
+// parks r and ppp in the consumed point's slot) against ec_madd, general and special cases, G1 and G2 fields
+template <class F> struct HostPoint {
+    typedef F Field;
+    F slot[2];
+    bool neg;
+    F ld_x() const { return slot[0]; }
+    F ld_y() const { return neg ? fneg(slot[1]) : slot[1]; }
+    bool is_zero() const { return slot[0].is_zero() && slot[1].is_zero(); }
+    Affine<F> get() const { Affine<F> a; a.x = ld_x(); a.y = ld_y(); return a; }
+    void st_scratch(int i, const F &v) { slot[i] = v; }
+    F ld_scratch(int i) const { return slot[i]; }
+};
+static Fq rndf(std::mt19937_64 &g, const Fq *) { return rnd<Fq>(g, g() % 12 < 8 ? 0 : g() % 6); }
+static Fq2 rndf(std::mt19937_64 &g, const Fq2 *) { Fq2 r; r.a = rndf(g, (const Fq *)0); r.b = rndf(g, (const Fq *)0); return r; }
+template <class F> int run_madd(const char *name, long iters) {
+    std::mt19937_64 g(4242);
+    long bad = 0;
+    for (long it = 0; it < iters; it++) {
+        Affine<F> q;
+        q.x = rndf(g, (const F *)0); q.y = rndf(g, (const F *)0);
+        Xyzz<F> a;
+        a.x = rndf(g, (const F *)0); a.y = rndf(g, (const F *)0); a.zz = rndf(g, (const F *)0); a.zzz = rndf(g, (const F *)0);
+        bool neg = g() & 1;
+        switch (it % 8) {
+            case 1: a = Xyzz<F>::zero(); break;                         // empty running sum
+            case 2: q.x = F::zero(); q.y = F::zero(); break;            // point at infinity
+            case 3: a = Xyzz<F>::from_affine(q); neg = false; break;    // same point: doubling
+            case 4: a = Xyzz<F>::from_affine(q); a.y = fneg(a.y); neg = false; break;   // opposite points
+            case 5: a = Xyzz<F>::from_affine(q); neg = true; break;     // opposite through the sign bit
+            default: break;
+        }
+        Affine<F> qs = q;
+        if (neg) qs.y = fneg(qs.y);
+        Xyzz<F> want = a;
+        ec_madd(want, qs);
+        RegAcc<F> acc;
+        acc.p = a;
+        HostPoint<F> hp;
+        hp.slot[0] = q.x; hp.slot[1] = q.y; hp.neg = neg;
+        ec_madd_acc_pt(acc, hp);
+        Xyzz<F> got = acc.get();
+        if (got.x != want.x || got.y != want.y || got.zz != want.zz || got.zzz != want.zzz) bad++;
+    }
+    printf("%s: bad=%ld\n", name, bad);
+    return bad != 0;
+}
+
 int main(int argc, char **argv) {
     long it = argc > 1 ? atol(argv[1]) : 1000000;
-    return run<Fq>("Fq", it) | run<Fr>("Fr", it) | run2(it);
+    return run<Fq>("Fq", it) | run<Fr>("Fr", it) | run2(it) | run_madd<Fq>("madd_pt G1", it / 4) | run_madd<Fq2>("madd_pt G2", it / 8);
 }
