@@ -64,7 +64,8 @@ int b200_msm_g2_dev(b200_ctx *ctx, const void *d_bases_affine, const void *d_sca
                     uint32_t scalar_size, uint64_t n, void *out_xyzz256);
 /* window size override for experiments (0 = automatic) */
 void b200_set_msm_window(b200_ctx *ctx, int c_bits);
-/* tuning knobs for experiments: "msm_window", "acc_smem" (-1 auto / 0 registers / 1 shared memory),
+/* tuning knobs for experiments: "msm_window", "acc_smem" (-1 auto / 0 registers / 1 running sum in shared memory /
+ * 2 G2 only: running sum and cp.async-staged points in shared memory),
  * "precomp" (-1 auto / 0 off / 1 on: per-window precomputed tables for resident zkeys), "precomp_c",
  * "h_streams" (1 / 3: a, b, c transform chains on one or three streams), "g2_minb", "warm_max", "reduce_l",
  * "reduce_l_g2", "tree_threads" */

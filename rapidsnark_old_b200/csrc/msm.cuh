@@ -722,7 +722,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     if (!side) { ctx->err = "msm: cannot create the side stream"; return B200_ERR_CUDA; }
     const bool g2 = sizeof(F) != 32;
     const u32 tree_threads = ctx->opt_tree_threads > 0 ? (u32)ctx->opt_tree_threads : (g2 ? 64u : 128u);
-    const bool acc_smem = ctx->opt_acc_smem > 0;   // measured on B200: registers win for both groups
+    const bool acc_smem = ctx->opt_acc_smem == 1;  // measured on B200: registers win for both groups (2 = staged G2 variant)
     const size_t acc_smem_bytes = 128 * sizeof(Pt);
     static const int env_g2_minb = getenv("B200_G2_MINB") ? atoi(getenv("B200_G2_MINB")) : 0;   // experiments
     const int g2_minb = ctx->opt_g2_minb ? ctx->opt_g2_minb : env_g2_minb ? env_g2_minb : (B200_G2_HOT_CALLS ? 3 : 2);
