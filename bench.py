@@ -111,6 +111,14 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def field_backend(o):
+    """Which Montgomery product the CPU oracle runs: ADX assembly like the reference's generated routines, or C."""
+    try:
+        return "ADX assembly (mulx/adcx/adox)" if o.lib.oracle_field_backend() else "plain C (__int128 CIOS)"
+    except Exception:
+        return "plain C (__int128 CIOS)"
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -166,8 +174,9 @@ def run_reference(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "u256-mont", "data": "synthetic",
             "config": {"workload": "groth16 prove, BN254, 2^%d constraints, synthetic chain circuit" % log_n,
                        "n_vars": s.n_vars, "n_public": s.n_public, "n_coefs": s.n_coefs,
-                       "impl_detail": "reference templates (curve/multiexp/fft/groth16) compiled from /root/reference "
-                                      "over a restated Fq/Fr field, OpenMP" if kind == "reference" else "plain-C oracle port"},
+                       "impl_detail": ("reference templates (curve/multiexp/fft/groth16) compiled from /root/reference "
+                                       "over a restated Fq/Fr field, OpenMP" if kind == "reference" else "plain-C oracle port") +
+                                      "; field product: " + field_backend(o)},
             "cpu_baseline": {"value": round(ms, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(ms, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -359,7 +368,8 @@ def cpu_baseline(s):
             (67890).to_bytes(32, "little"))
     ms = (time.perf_counter() - t0) * 1e3
     return {"value": round(ms, 1), "unit": UNIT, "cores": o.threads(), "kind": kind,
-            "sample": "one full 2^%d proof (H pipeline + 5 MSMs + blinding), same inputs, cold" % s.log_n}
+            "sample": "one full 2^%d proof (H pipeline + 5 MSMs + blinding), same inputs, cold; field product: %s"
+                      % (s.log_n, field_backend(o))}
 
 
 def main():

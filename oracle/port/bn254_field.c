@@ -4,6 +4,22 @@
  * pre-generated sample ffiasm/benchmark/fr.asm:7098-7103 for the Fq prime).
  */
 #include "bn254_field.h"
+#include <stdlib.h>
+
+/* Field backend: 1 = ADX assembly (bn254_mmul_adx.S) when the CPU has ADX + BMI2 and ORACLE_NO_ADX is not set,
+ * 0 = the plain-C CIOS below.  Both are canonical and bit-identical (tests/test_oracle.py). */
+int oracle_use_adx = 0;
+__attribute__((constructor)) static void oracle_pick_backend(void)
+{
+    __builtin_cpu_init();
+    oracle_use_adx = __builtin_cpu_supports("adx") && __builtin_cpu_supports("bmi2") && !getenv("ORACLE_NO_ADX");
+}
+int oracle_field_backend(void) { return oracle_use_adx; }
+void oracle_set_field_backend(int adx)
+{
+    __builtin_cpu_init();
+    oracle_use_adx = adx && __builtin_cpu_supports("adx") && __builtin_cpu_supports("bmi2");
+}
 
 /* ---- Fq : 21888242871839275222246405745257275088696311157297823662689037894645226208583 */
 static const uint64_t FQ_Q[4]  = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};

@@ -35,6 +35,11 @@ extern "C" {
 ORACLE_DECL_FIELD(Fq)
 ORACLE_DECL_FIELD(Fr)
 
+/* field backend of rawMMul / rawMSquare: 1 = ADX assembly (bn254_mmul_adx.S), 0 = plain C; picked at load time */
+extern int oracle_use_adx;
+int oracle_field_backend(void);
+void oracle_set_field_backend(int adx);
+
 #ifdef __cplusplus
 }
 #endif

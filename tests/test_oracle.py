@@ -37,9 +37,22 @@ def _critical(p):
     return sorted(vals)
 
 
+@pytest.mark.parametrize("backend", ["adx", "c"])
 @pytest.mark.parametrize("name,p", [("Fq", bn.Q), ("Fr", bn.R_ORDER)])
-def test_field_ops_against_bigints(name, p):
+def test_field_ops_against_bigints(name, p, backend):
+    """Both backends of the oracle's Montgomery product - the ADX assembly (mulx / adcx / adox, like the reference's
+    generated routines) and the plain-C CIOS - against Python big integers on the critical numbers."""
     lib = _field_lib()
+    lib.oracle_set_field_backend(1 if backend == "adx" else 0)
+    if backend == "adx" and not lib.oracle_field_backend():
+        pytest.skip("CPU without ADX / BMI2")
+    try:
+        _field_ops_check(lib, name, p)
+    finally:
+        lib.oracle_set_field_backend(1)
+
+
+def _field_ops_check(lib, name, p):
     vals = _critical(p)
     rinv = pow(bn.MONT_R, -1, p)
     buf = lambda: ctypes.create_string_buffer(32)
