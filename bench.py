@@ -84,15 +84,19 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def build_inputs(log_n, seed, g1_many, g2_many, fast=True):
+def build_inputs(log_n, seed, g1_many, g2_many, fast=True, shard=None):
     """The synthetic circuit of SURVEY.md Appendix C.  fast: scalars from the library's host routine (FastSynth,
-    identical values, seconds instead of minutes at 2^24); the point makers must then accept packed bytes."""
+    identical values, seconds instead of minutes at 2^24); the point makers must then accept packed bytes.
+    shard = (rank, world): only this rank's slices of the point tables are generated (s.shard_points)."""
     from rapidsnark_old_b200 import synth
     t = time.time()
     s = synth.FastSynth(log_n, seed) if fast else synth.Synth(log_n, seed)
     log("[bench] synthetic circuit 2^%d: scalars in %.1fs" % (log_n, time.time() - t))
     t = time.time()
-    s.build_points(g1_many, g2_many)
+    if shard:
+        s.build_shard_points(g1_many, g2_many, *shard)
+    else:
+        s.build_points(g1_many, g2_many)
     log("[bench] point tables in %.1fs" % (time.time() - t))
     return s
 
@@ -200,8 +204,14 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = b200.Context(local)
     log_n = args.log_n
-    s = build_inputs(log_n, 2, *gpu_point_makers(ctx))
-    p, vk = s.points, s.vk
+    # big circuits on several GPUs: every rank generates only the table slices it uploads (2^26: 24 GB of tables)
+    shard_inputs = world > 1 and (args.shard_inputs or log_n >= 23)
+    s = build_inputs(log_n, 2, *gpu_point_makers(ctx), shard=(rank, world) if shard_inputs else None)
+    if shard_inputs:
+        p = {k: s.shard_table_address(k) for k in ("A", "B1", "B2", "C", "H")}
+    else:
+        p = s.points
+    vk = s.vk
     emu = args.emulate_shards if world == 1 else 0      # tuning aid: this GPU plays rank 0 of `emu` (no collective,
     for kv in args.opt:                                  # result unchecked); never used for a reported line
         k, v = kv.split("=")
@@ -380,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-inputs", action="store_true",
+                    help="N > 1: generate only this rank's slices of the point tables (automatic from 2^23)")
     ap.add_argument("--replicate-h", action="store_true", help="N > 1: every rank runs the whole H pipeline (A/B)")
     ap.add_argument("--emulate-shards", type=int, default=0, help="tuning only: time rank 0 of K shards on one GPU")
     ap.add_argument("--opt", nargs="*", default=[], help="tuning only: library options name=value (b200_set_option)")

@@ -294,6 +294,41 @@ class FastSynth:
 
     build_points = Synth.build_points
 
+    # ---- one shard's slices only (multi-GPU runs of big circuits: 2^26 tables are 24 GB, times eight ranks)
+    def build_shard_points(self, g1_mul_many, g2_mul_many, index, count):
+        """Point tables restricted to what b200_zkey_upload reads for shard `index` of `count` (same partition rule:
+        [len * index / count, len * (index + 1) / count) of the witness-indexed tables and of H).  Fills
+        self.shard_points = {name: (bytes, first_point_index)} and self.vk; see shard_table_address()."""
+        V, P, n = self.n_vars, self.n_public, self.n
+        lo, hi = V * index // count, V * (index + 1) // count
+        hlo, hhi = n * index // count, n * (index + 1) // count
+        skip = P + 1
+        clo, chi = max(lo, skip) - skip, max(hi, skip) - skip          # C table: signals skip .. V-1
+        cut = lambda b, a, z: b[32 * a:32 * z]
+        self.shard_points = {
+            "A": (g1_mul_many(cut(self.A_tau, lo, hi)), lo),
+            "B1": (g1_mul_many(cut(self.B_tau, lo, hi)), lo),
+            "B2": (g2_mul_many(cut(self.B_tau, lo, hi)), lo),
+            "C": (g1_mul_many(cut(self.c_scalars, clo, chi)), clo),
+            "H": (g1_mul_many(cut(self.h_scalars_tbl, hlo, hhi)), hlo),
+        }
+        vk1 = g1_mul_many([self.alpha, self.beta, self.delta])
+        vk2 = g2_mul_many([self.beta, self.gamma, self.delta])
+        self.vk = {"alpha1": vk1[0:64], "beta1": vk1[64:128], "delta1": vk1[128:192],
+                   "beta2": vk2[0:128], "gamma2": vk2[128:256], "delta2": vk2[256:384]}
+        return self
+
+    def shard_table_address(self, name):
+        """Address to hand to b200_zkey_upload as the table's base: the library only reads this shard's range, which
+        starts first_point_index points after the base, so base = address(slice) - first_point_index * point_size.
+        (The buffer is kept alive in self._shard_keep.)"""
+        import ctypes
+        data, first = self.shard_points[name]
+        size = 128 if name == "B2" else 64
+        buf = ctypes.create_string_buffer(data, max(len(data), 1))
+        self.__dict__.setdefault("_shard_keep", []).append(buf)
+        return ctypes.addressof(buf) - first * size
+
 
 # ----------------------------------------------------------------------------- iden3 binfile writers
 def _binfile(magic, version, sections):

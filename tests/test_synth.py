@@ -84,3 +84,33 @@ def test_bench_inputs_and_exponent_check_on_cpu():
     bad[200] ^= 1
     with pytest.raises(AssertionError):
         bench.check_known_dlogs(b200, s, msms, bytes(bad), r32, s32)
+
+
+@pytest.mark.parametrize("count", [1, 2, 3, 8])
+def test_shard_only_point_tables_are_slices_of_the_full_ones(count):
+    """FastSynth.build_shard_points (big multi-GPU runs generate only their own slices) against the full tables, and
+    the base-address arithmetic used to hand a slice to b200_zkey_upload."""
+    import ctypes
+    g1m, g2m = synth_util.oracle_point_makers()
+    unpack = lambda ks: [int.from_bytes(ks[i:i + 32], "little") for i in range(0, len(ks), 32)] \
+        if isinstance(ks, (bytes, bytearray)) else ks
+    mk1, mk2 = (lambda ks: g1m(unpack(ks))), (lambda ks: g2m(unpack(ks)))
+    full = synth.FastSynth(5, 2).build_points(mk1, mk2)
+    V, P, n = full.n_vars, full.n_public, full.n
+    for index in range(count):
+        sh = synth.FastSynth(5, 2).build_shard_points(mk1, mk2, index, count)
+        assert sh.vk == full.vk
+        lo, hi = V * index // count, V * (index + 1) // count
+        hlo, hhi = n * index // count, n * (index + 1) // count
+        skip = P + 1
+        clo, chi = max(lo, skip) - skip, max(hi, skip) - skip
+        assert sh.shard_points["A"] == (full.points["A"][64 * lo:64 * hi], lo)
+        assert sh.shard_points["B1"] == (full.points["B1"][64 * lo:64 * hi], lo)
+        assert sh.shard_points["B2"] == (full.points["B2"][128 * lo:128 * hi], lo)
+        assert sh.shard_points["C"] == (full.points["C"][64 * clo:64 * chi], clo)
+        assert sh.shard_points["H"] == (full.points["H"][64 * hlo:64 * hhi], hlo)
+        for name, size, first, cnt in (("A", 64, lo, hi - lo), ("B2", 128, lo, hi - lo), ("C", 64, clo, chi - clo),
+                                       ("H", 64, hlo, hhi - hlo)):
+            base = sh.shard_table_address(name)
+            got = ctypes.string_at(base + first * size, cnt * size)
+            assert got == sh.shard_points[name][0]

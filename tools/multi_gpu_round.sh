@@ -13,6 +13,11 @@ wait
 ( CUDA_VISIBLE_DEVICES=4 run 100 python tools/msm_bench.py --log-n 16 18 20 22 24 --iters 3 --cpu-max-log-n 22 > gpurun_out/r01_msm_sweep_g1_n1_cpu.jsonl 2> gpurun_out/msm_n1.log ) &
 wait
 run 120 $TR --nproc-per-node 8 --master-port 29607 tools/msm_bench.py --log-n 20 22 24 26 28 --iters 3 > gpurun_out/r01_msm_sweep_g1_n8.jsonl 2> gpurun_out/msm_n8.log
+if [ "$1" = "with26" ]; then
+  # BASELINE config 4: 2^26 constraints sharded over 8 GPUs; every rank generates only its own table slices
+  run 900 $TR --nproc-per-node 8 --master-port 29608 bench.py --gpus 8 --log-n 26 --steps 3 --warmup 3 > gpurun_out/bench_2_26_n8.json 2> gpurun_out/bench_2_26_n8.log
+  tail -c 1200 gpurun_out/bench_2_26_n8.json; tail -3 gpurun_out/bench_2_26_n8.log
+fi
 for f in gpurun_out/r01_bench_n8.json gpurun_out/r01_bench_n8_replicated_h.json gpurun_out/r01_bench_n4.json gpurun_out/r01_bench_n2.json; do python - "$f" <<'PY'
 import json,sys
 try:
