@@ -166,6 +166,14 @@ void b200_host_g2_mul(void *r_xyzz, const void *base_affine, const void *scalar,
  *      Montgomery, exactly the fields of Groth16::Proof (groth16.hpp:14-24) */
 void b200_groth16_finalize(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
                            const void *delta1, const void *delta2, const void *r32, const void *s32, void *out256);
+/* The same in two steps, so that the host work which depends only on the verification key and r, s (three G1 and
+ * one G2 scalar multiplication - most of it) can run on a host thread WHILE the GPU computes the MSMs:
+ * prep640 = r*delta1 | s*delta1 | (rs)*delta1 (G1 XYZZ) | s*delta2 (G2 XYZZ).  finalize = prepare + finalize_prepared. */
+void b200_groth16_blind_prepare(const void *delta1, const void *delta2, const void *r32, const void *s32, void *prep640);
+void b200_groth16_finalize_prepared(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                                    const void *prep640, const void *r32, const void *s32, void *out256);
+/* sum of n gathered per-GPU partial records (n x 768 bytes, layout of b200_prove_msms) into one */
+void b200_host_fold_partials(const void *parts768, int n, void *out768);
 /* canonical decimal string (<= 78 digits + NUL) of a Montgomery-form Fq element (RawFq::toString) */
 void b200_fq_to_decimal(const void *mont32, char *out80);
 

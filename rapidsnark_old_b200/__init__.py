@@ -30,7 +30,8 @@ EXPORTS = [
     "b200_ntt_fr", "b200_ntt_fr_dev",
     "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
     "b200_prove_begin", "b200_prove_finish", "b200_exchange_polys",
-    "b200_groth16_finalize", "b200_fq_to_decimal",
+    "b200_groth16_finalize", "b200_groth16_blind_prepare", "b200_groth16_finalize_prepared", "b200_host_fold_partials",
+    "b200_fq_to_decimal",
     "b200_fixed_base_g1", "b200_fixed_base_g2", "b200_synth_chain",
     "b200_host_fq_mul", "b200_host_fq_add", "b200_host_fq_sub", "b200_host_fq_neg", "b200_host_fq_inv",
     "b200_host_fr_mul", "b200_host_fr_add", "b200_host_fr_sub", "b200_host_fr_neg", "b200_host_fr_inv",
@@ -89,6 +90,9 @@ def lib():
         L.b200_stream.restype = _vp
         L.b200_stream.argtypes = [_vp]
         L.b200_groth16_finalize.argtypes = [_vp] * 9
+        L.b200_groth16_blind_prepare.argtypes = [_vp] * 5
+        L.b200_groth16_finalize_prepared.argtypes = [_vp] * 8
+        L.b200_host_fold_partials.argtypes = [_vp, _int, _vp]
         L.b200_fq_to_decimal.argtypes = [_vp, _vp]
         L.b200_fixed_base_g1.argtypes = [_vp, _vp, _vp, _u64, _vp]
         L.b200_fixed_base_g2.argtypes = [_vp, _vp, _vp, _u64, _vp]
@@ -160,12 +164,24 @@ def exchange_polys(zkeys):
 
 def fold_partials(parts768):
     """Sum per-GPU partial results of prove_msms (pih, pi_a, pib1 | pi_b | pi_c) into one 768-byte record."""
-    acc = bytearray(parts768[0])
-    for p in parts768[1:]:
-        for off, size, add in ((0, 128, host_g1_add), (128, 128, host_g1_add), (256, 128, host_g1_add),
-                               (384, 256, host_g2_add), (640, 128, host_g1_add)):
-            acc[off:off + size] = add(bytes(acc[off:off + size]), bytes(p[off:off + size]))
-    return bytes(acc)
+    out = ctypes.create_string_buffer(768)
+    lib().b200_host_fold_partials(b"".join(bytes(p) for p in parts768), len(parts768), out)
+    return out.raw
+
+
+def groth16_blind_prepare(vk, r32, s32):
+    """The part of the blinding that needs only the key and r, s (r*delta1, s*delta1, rs*delta1, s*delta2): run it on
+    a host thread while the GPU works (ctypes releases the GIL), then groth16_finalize_prepared."""
+    out = ctypes.create_string_buffer(640)
+    lib().b200_groth16_blind_prepare(_ptr(vk["delta1"]), _ptr(vk["delta2"]), _ptr(r32), _ptr(s32), out)
+    return out.raw
+
+
+def groth16_finalize_prepared(msms768, vk, prep640, r32, s32):
+    out = ctypes.create_string_buffer(256)
+    lib().b200_groth16_finalize_prepared(_ptr(msms768), _ptr(vk["alpha1"]), _ptr(vk["beta1"]), _ptr(vk["beta2"]),
+                                         _ptr(prep640), _ptr(r32), _ptr(s32), out)
+    return out.raw
 
 
 # ----------------------------------------------------------------------------- device context

@@ -11,7 +11,7 @@ Works with the gloo backend on CPU tensors too (tests)."""
 import torch
 import torch.distributed as dist
 
-from . import fold_partials, groth16_finalize
+from . import fold_partials, groth16_finalize, groth16_finalize_prepared
 
 
 def shard_range(length, index, count):
@@ -76,8 +76,11 @@ def prove_msms_distributed(zk, wtns, on_device, domain_size, device, group=None)
     return zk.prove_finish()
 
 
-def finish_proof(part768, vk, r32, s32, device=None, group=None):
-    """partial MSM results of this rank -> (folded 768-byte record, proof A|B|C 256 bytes) on every rank."""
+def finish_proof(part768, vk, r32, s32, device=None, group=None, prep640=None):
+    """partial MSM results of this rank -> (folded 768-byte record, proof A|B|C 256 bytes) on every rank.
+    prep640: result of groth16_blind_prepare(vk, r32, s32) computed on a host thread while the GPU worked."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         part768 = fold_partials(all_gather_partials(part768, device, group))
+    if prep640 is not None:
+        return part768, groth16_finalize_prepared(part768, vk, prep640, r32, s32)
     return part768, groth16_finalize(part768, vk, r32, s32)

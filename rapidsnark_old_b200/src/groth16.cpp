@@ -114,6 +114,19 @@ std::unique_ptr<Proof<Engine>> Prover<Engine>::prove(typename Engine::FrElement 
     const size_t G = gpus.size();
     std::vector<uint8_t> parts(768 * G);
     std::vector<int> rcs(G, 0);
+    // r, s: 31 random bytes each, top byte zero (groth16.cpp:213-217).  Drawn first: the part of the blinding that
+    // needs only the key and r, s (r*delta1, s*delta1, rs*delta1, s*delta2 - three G1 and one G2 scalar
+    // multiplication, most of the host work of a proof) runs on a host thread while the GPUs compute the MSMs.
+    uint8_t r[32] = {0}, s[32] = {0};
+    if (fixedRS) {
+        memcpy(r, fixedR, 32);
+        memcpy(s, fixedS, 32);
+    } else {
+        if (getrandom(r, 31, 0) != 31 || getrandom(s, 31, 0) != 31) throw std::runtime_error("getrandom failed");
+    }
+    uint8_t prep[640];
+    std::thread blind([&]() { b200_groth16_blind_prepare(&vk_delta1, &vk_delta2, r, s, prep); });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joinBlind{blind};
     if (G == 1) {
         rcs[0] = b200_prove_msms(gpus[0].ctx, gpus[0].zk, wtns, parts.data());
     } else if (getenv("B200_REPLICATE_H")) {     // every GPU repeats the whole H pipeline (A/B, no exchange)
@@ -180,16 +193,9 @@ std::unique_ptr<Proof<Engine>> Prover<Engine>::prove(typename Engine::FrElement 
     int k = b200_last_phase_ms(gpus[0].ctx, ms, 16);
     for (int i = 0; i < k; i++) lastPhases.emplace_back(b200_phase_name(i), ms[i]);
 
-    // r, s: 31 random bytes each, top byte zero (groth16.cpp:213-217)
-    uint8_t r[32] = {0}, s[32] = {0};
-    if (fixedRS) {
-        memcpy(r, fixedR, 32);
-        memcpy(s, fixedS, 32);
-    } else {
-        if (getrandom(r, 31, 0) != 31 || getrandom(s, 31, 0) != 31) throw std::runtime_error("getrandom failed");
-    }
+    blind.join();
     uint8_t out[256];
-    b200_groth16_finalize(lastMsms, &vk_alpha1, &vk_beta1, &vk_beta2, &vk_delta1, &vk_delta2, r, s, out);
+    b200_groth16_finalize_prepared(lastMsms, &vk_alpha1, &vk_beta1, &vk_beta2, prep, r, s, out);
     std::unique_ptr<Proof<Engine>> p(new Proof<Engine>());
     memcpy(&p->A, out, 64);
     memcpy(&p->B, out + 64, 128);

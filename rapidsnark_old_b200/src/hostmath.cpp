@@ -43,39 +43,83 @@ void host_msm_finish_g2(const void *planes, int nsets, int nplanes, int L, int n
 
 // Blinding + finalisation of src/groth16.cpp:209-253 with explicit r, s (32-byte little-endian, used
 // un-reduced like the reference's 248-bit values): in = pih, pi_a, pib1 (G1 XYZZ), pi_b (G2 XYZZ), pi_c.
-void groth16_finalize(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
-                      const void *delta1, const void *delta2, const uint8_t *r32, const uint8_t *s32, void *out256) {
-    const uint8_t *m = (const uint8_t *)msms768;
-    HG1 pih, pi_a, pib1, pi_c;
-    HG2 pi_b;
-    memcpy(&pih, m, 128); memcpy(&pi_a, m + 128, 128); memcpy(&pib1, m + 256, 128);
-    memcpy(&pi_b, m + 384, 256); memcpy(&pi_c, m + 640, 128);
-    HG1Affine a1, b1, d1;
-    HG2Affine b2, d2;
-    memcpy(&a1, alpha1, 64); memcpy(&b1, beta1, 64); memcpy(&d1, delta1, 64);
-    memcpy(&b2, beta2, 128); memcpy(&d2, delta2, 128);
-
-    ec_madd(pi_a, a1);                                   // pi_a += alpha1 + r*delta1      (:222-224)
-    ec_add(pi_a, scalar_mul(d1, r32, 32));
-    ec_madd(pi_b, b2);                                   // pi_b += beta2 + s*delta2       (:226-228)
-    ec_add(pi_b, scalar_mul(d2, s32, 32));
-    ec_madd(pib1, b1);                                   // pib1 += beta1 + s*delta1       (:230-232)
-    ec_add(pib1, scalar_mul(d1, s32, 32));
-    ec_add(pi_c, pih);                                   // pi_c += pih                    (:234)
-    HG1Affine pa = ec_to_affine(pi_a), pb1 = ec_to_affine(pib1);
-    ec_add(pi_c, scalar_mul(pa, s32, 32));               // + s*pi_a                       (:236-237)
-    ec_add(pi_c, scalar_mul(pb1, r32, 32));              // + r*pib1                       (:239-240)
+//
+// Split in two so that the part which depends only on the verification key and r, s - three G1 and one G2 scalar
+// multiplication, most of the host work of a proof - can run on a host thread WHILE the GPU computes the MSMs:
+//   prepare : r*delta1 | s*delta1 | (rs)*delta1 | s*delta2                              (3 x 128 + 256 bytes, XYZZ)
+//   finish  : the additions, s*pi_a + r*pib1 and the affine conversions, once the MSM results are there
+// groth16_finalize = prepare + finish.  The proof's affine coordinates do not depend on the order of evaluation.
+void groth16_blind_prepare(const void *delta1, const void *delta2, const uint8_t *r32, const uint8_t *s32, void *prep640) {
+    HG1Affine d1;
+    HG2Affine d2;
+    memcpy(&d1, delta1, 64);
+    memcpy(&d2, delta2, 128);
     HFr r, s;                                            // rs = r*s mod r                 (:242-243)
     memcpy(&r, r32, 32); memcpy(&s, s32, 32);
     HFr rs = hfp_to_mont(fmul(r, s));
     uint8_t rsb[32];
     memcpy(rsb, &rs, 32);
-    ec_add(pi_c, ec_neg(scalar_mul(d1, rsb, 32)));       // - (rs)*delta1                  (:245-246)
+    HG1 rd1 = scalar_mul(d1, r32, 32), sd1 = scalar_mul(d1, s32, 32), rsd1 = scalar_mul(d1, rsb, 32);
+    HG2 sd2 = scalar_mul(d2, s32, 32);
+    uint8_t *o = (uint8_t *)prep640;
+    memcpy(o, &rd1, 128); memcpy(o + 128, &sd1, 128); memcpy(o + 256, &rsd1, 128); memcpy(o + 384, &sd2, 256);
+}
+
+void groth16_finalize_prepared(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                               const void *prep640, const uint8_t *r32, const uint8_t *s32, void *out256) {
+    const uint8_t *m = (const uint8_t *)msms768, *pp = (const uint8_t *)prep640;
+    HG1 pih, pi_a, pib1, pi_c, rd1, sd1, rsd1;
+    HG2 pi_b, sd2;
+    memcpy(&pih, m, 128); memcpy(&pi_a, m + 128, 128); memcpy(&pib1, m + 256, 128);
+    memcpy(&pi_b, m + 384, 256); memcpy(&pi_c, m + 640, 128);
+    memcpy(&rd1, pp, 128); memcpy(&sd1, pp + 128, 128); memcpy(&rsd1, pp + 256, 128); memcpy(&sd2, pp + 384, 256);
+    HG1Affine a1, b1;
+    HG2Affine b2;
+    memcpy(&a1, alpha1, 64); memcpy(&b1, beta1, 64); memcpy(&b2, beta2, 128);
+
+    ec_madd(pi_a, a1);                                   // pi_a += alpha1 + r*delta1      (:222-224)
+    ec_add(pi_a, rd1);
+    ec_madd(pi_b, b2);                                   // pi_b += beta2 + s*delta2       (:226-228)
+    ec_add(pi_b, sd2);
+    ec_madd(pib1, b1);                                   // pib1 += beta1 + s*delta1       (:230-232)
+    ec_add(pib1, sd1);
+    ec_add(pi_c, pih);                                   // pi_c += pih                    (:234)
+    HG1Affine pa = ec_to_affine(pi_a), pb1 = ec_to_affine(pib1);
+    ec_add(pi_c, scalar_mul(pa, s32, 32));               // + s*pi_a                       (:236-237)
+    ec_add(pi_c, scalar_mul(pb1, r32, 32));              // + r*pib1                       (:239-240)
+    ec_add(pi_c, ec_neg(rsd1));                          // - (rs)*delta1                  (:245-246)
 
     HG2Affine B = ec_to_affine(pi_b);
     HG1Affine C = ec_to_affine(pi_c);
     uint8_t *o = (uint8_t *)out256;
     memcpy(o, &pa, 64); memcpy(o + 64, &B, 128); memcpy(o + 192, &C, 64);
+}
+
+void groth16_finalize(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                      const void *delta1, const void *delta2, const uint8_t *r32, const uint8_t *s32, void *out256) {
+    uint8_t prep[640];
+    groth16_blind_prepare(delta1, delta2, r32, s32, prep);
+    groth16_finalize_prepared(msms768, alpha1, beta1, beta2, prep, r32, s32, out256);
+}
+
+// sum of n per-GPU partial records (pih, pi_a, pib1 | pi_b | pi_c), one call instead of 5 (n - 1) from the binding
+void fold_partials(const void *parts768, int n, void *out768) {
+    const uint8_t *p = (const uint8_t *)parts768;
+    HG1 g1[4];
+    HG2 g2;
+    static const int off1[4] = {0, 128, 256, 640};
+    for (int k = 0; k < 4; k++) memcpy(&g1[k], p + off1[k], 128);
+    memcpy(&g2, p + 384, 256);
+    for (int i = 1; i < n; i++) {
+        const uint8_t *q = p + (size_t)768 * i;
+        for (int k = 0; k < 4; k++) { HG1 t; memcpy(&t, q + off1[k], 128); ec_add(g1[k], t); }
+        HG2 t2;
+        memcpy(&t2, q + 384, 256);
+        ec_add(g2, t2);
+    }
+    uint8_t *o = (uint8_t *)out768;
+    for (int k = 0; k < 4; k++) memcpy(o + off1[k], &g1[k], 128);
+    memcpy(o + 384, &g2, 256);
 }
 
 // canonical decimal string of a Montgomery-form Fq element (RawFq::toString, fr.cpp.ejs:202-213)
@@ -107,6 +151,14 @@ void b200_groth16_finalize(const void *msms768, const void *alpha1, const void *
                            const void *delta1, const void *delta2, const void *r32, const void *s32, void *out256) {
     b200::groth16_finalize(msms768, alpha1, beta1, beta2, delta1, delta2, (const uint8_t *)r32, (const uint8_t *)s32, out256);
 }
+void b200_groth16_blind_prepare(const void *delta1, const void *delta2, const void *r32, const void *s32, void *prep640) {
+    b200::groth16_blind_prepare(delta1, delta2, (const uint8_t *)r32, (const uint8_t *)s32, prep640);
+}
+void b200_groth16_finalize_prepared(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                                    const void *prep640, const void *r32, const void *s32, void *out256) {
+    b200::groth16_finalize_prepared(msms768, alpha1, beta1, beta2, prep640, (const uint8_t *)r32, (const uint8_t *)s32, out256);
+}
+void b200_host_fold_partials(const void *parts768, int n, void *out768) { b200::fold_partials(parts768, n, out768); }
 void b200_fq_to_decimal(const void *mont32, char *out80) { b200::fq_to_decimal(mont32, out80); }
 
 void b200_host_fq_mul(void *r, const void *a, const void *b) { st(r, fp_mul(ld<Fq>(a), ld<Fq>(b))); }

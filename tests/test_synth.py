@@ -60,6 +60,15 @@ def test_fast_synth_equals_python_synth(log_n, n_public):
     assert synth.count32(b.A_tau) == a.n_vars == synth.count32(a.A_tau)
 
 
+def _fold_by_single_adds(b200, parts):
+    acc = bytearray(parts[0])
+    for p in parts[1:]:
+        for off, size, add in ((0, 128, b200.host_g1_add), (128, 128, b200.host_g1_add), (256, 128, b200.host_g1_add),
+                               (384, 256, b200.host_g2_add), (640, 128, b200.host_g1_add)):
+            acc[off:off + size] = add(bytes(acc[off:off + size]), bytes(p[off:off + size]))
+    return bytes(acc)
+
+
 def test_bench_inputs_and_exponent_check_on_cpu():
     """bench.py's input builder (FastSynth + point makers fed packed bytes) and its in-the-exponent proof check,
     end to end on the CPU: the oracle plays the prover."""
@@ -77,9 +86,20 @@ def test_bench_inputs_and_exponent_check_on_cpu():
     p, vk = s.points, s.vk
     msms = o.prove_msms(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"],
                         p["H"], s.wtns_bytes())
-    r32, s32 = (12345).to_bytes(32, "little"), (67890).to_bytes(32, "little")
+    r32, s32 = bench.blinding_factors()
+    assert len(r32) == len(s32) == 32 and r32[31] == 0 and r32[30] != 0      # 248-bit values, like groth16.cpp:213-217
     proof = b200.groth16_finalize(msms, vk, r32, s32)
     bench.check_known_dlogs(b200, s, msms, proof, r32, s32)
+    # the split used by bench.py / the host prover: key-only part on a host thread, the rest after the MSMs
+    from concurrent.futures import ThreadPoolExecutor
+    from rapidsnark_old_b200 import dist as bdist
+    prep = ThreadPoolExecutor(max_workers=1).submit(b200.groth16_blind_prepare, vk, r32, s32)
+    folded, proof2 = bdist.finish_proof(msms, vk, r32, s32, prep640=prep.result())
+    assert folded == msms and proof2 == proof
+    assert proof == o.blind(msms, vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"], vk["delta2"], r32, s32)
+    assert b200.fold_partials([msms]) == msms
+    three = b200.fold_partials([msms, msms, msms])
+    assert o.msms_to_affine(three) == o.msms_to_affine(_fold_by_single_adds(b200, [msms, msms, msms]))
     bad = bytearray(proof)
     bad[200] ^= 1
     with pytest.raises(AssertionError):
