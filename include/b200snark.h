@@ -50,6 +50,10 @@ void *b200_stream(b200_ctx *ctx);
  * fills up to `cap` floats, returns how many; names via b200_phase_name(i) */
 int b200_last_phase_ms(b200_ctx *ctx, float *out, int cap);
 const char *b200_phase_name(int i);
+/* with option "timeline" = 1: every timed segment of the last call as a triple (phase index, start ms, end ms), times
+ * relative to the first segment's start, in issue order - segments of different streams overlap, so this, not the
+ * per-phase sums above, shows the critical path.  Fills up to cap floats (3 per segment); returns the segment count */
+int b200_last_timeline(b200_ctx *ctx, float *out, int cap);
 
 /* ---- MSM: replaces Curve::multiMulByScalar (curve.hpp:118-121) ---------------------------------- */
 /* host buffers in, XYZZ Montgomery out (any representative of the reference's result point) */
@@ -68,7 +72,7 @@ void b200_set_msm_window(b200_ctx *ctx, int c_bits);
  * 2 G2 only: running sum and cp.async-staged points in shared memory),
  * "precomp" (-1 auto / 0 off / 1 on: per-window precomputed tables for resident zkeys), "precomp_c",
  * "h_streams" (1 / 3: a, b, c transform chains on one or three streams), "g2_minb", "warm_max", "reduce_l",
- * "reduce_l_g2", "tree_threads" */
+ * "reduce_l_g2", "tree_threads", "timeline" (see b200_last_timeline) */
 int b200_set_option(b200_ctx *ctx, const char *name, int value);
 
 /* ---- NTT: replaces FFT<Fr>::fft / ifft (fft.hpp:24-25), natural order in and out ------------------ */

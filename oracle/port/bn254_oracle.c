@@ -265,6 +265,7 @@ static void ifft_run(const fft_t *f, fr_t *a, uint64_t n)                       
 
 /* ------------------------------------------------------------------ exported API */
 int orc_threads(void) { return omp_get_max_threads(); }
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 void orc_g1_msm(const void *bases, const void *scalars, uint32_t scalarSize, uint32_t n, void *out)
 {

@@ -52,6 +52,8 @@ static FFT<RawFr> *fft_for(uint64_t maxDomain)
 extern "C" {
 
 int ref_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: bench.py --impl reference asks for all host cores explicitly */
+void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 void ref_g1_msm(const void *bases, const void *scalars, uint32_t scalarSize, uint32_t n, void *out)
 {
@@ -261,5 +263,29 @@ void ref_groth16_prove(uint32_t nVars, uint32_t nPublic, uint32_t domainSize, ui
     uint8_t *out = (uint8_t *)out_proof256;
     memcpy(out, &proof->A, 64); memcpy(out + 64, &proof->B, 128); memcpy(out + 192, &proof->C, 64);
 }
+
+/* The same two calls kept apart, so that a caller timing proofs can build the Prover once (the reference's
+ * server mode does: src/fullprover.cpp:43-59 builds it at start-up, :155 proves per request).  makeProver's FFT
+ * root table (fft.cpp:32-115) is then outside the per-proof time, exactly like this repo's b200_zkey_upload. */
+void *ref_make_prover(uint32_t nVars, uint32_t nPublic, uint32_t domainSize, uint64_t nCoefs,
+                      const void *alpha1, const void *beta1, const void *beta2, const void *delta1,
+                      const void *delta2, const void *coefs_section, const void *pointsA,
+                      const void *pointsB1, const void *pointsB2, const void *pointsC, const void *pointsH)
+{
+    auto prover = Groth16::makeProver<Engine>(nVars, nPublic, domainSize, nCoefs, (void *)alpha1, (void *)beta1,
+                                              (void *)beta2, (void *)delta1, (void *)delta2, (void *)coefs_section,
+                                              (void *)pointsA, (void *)pointsB1, (void *)pointsB2, (void *)pointsC,
+                                              (void *)pointsH);
+    return prover.release();
+}
+
+void ref_prover_prove(void *prover, const void *wtns, void *out_proof256)
+{
+    auto proof = ((Groth16::Prover<Engine> *)prover)->prove((FrElement *)wtns);
+    uint8_t *out = (uint8_t *)out_proof256;
+    memcpy(out, &proof->A, 64); memcpy(out + 64, &proof->B, 128); memcpy(out + 192, &proof->C, 64);
+}
+
+void ref_free_prover(void *prover) { delete (Groth16::Prover<Engine> *)prover; }
 
 } /* extern "C" */

@@ -12,6 +12,7 @@ Interface mirrored (reference iden3/rapidsnark-old):
 """
 import ctypes
 import os
+import weakref
 
 # more hardware work queues than the default 8, so that the library's streams (main, H, one per in-flight MSM) and
 # torch's / NCCL's never share one and serialise; only effective before the process's first CUDA call
@@ -26,6 +27,7 @@ _u32, _u64, _vp, _int = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctype
 
 EXPORTS = [
     "b200_init", "b200_free", "b200_last_error", "b200_launch_count", "b200_last_phase_ms", "b200_phase_name",
+    "b200_last_timeline",
     "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window", "b200_set_option",
     "b200_ntt_fr", "b200_ntt_fr_dev",
     "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
@@ -98,6 +100,7 @@ def lib():
         L.b200_fixed_base_g2.argtypes = [_vp, _vp, _vp, _u64, _vp]
         L.b200_synth_chain.argtypes = [_u32, _u32] + [_vp] * 13
         L.b200_last_phase_ms.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), _int]
+        L.b200_last_timeline.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), _int]
         _lib = L
     return _lib
 
@@ -189,6 +192,7 @@ class ZKey:
     def __init__(self, ctx, handle, desc_keepalive):
         self.ctx, self.handle, self._keep = ctx, handle, desc_keepalive
         self.domain_size = desc_keepalive[0].domain_size
+        ctx._zkeys.add(self)      # b200_zkey_free needs the context alive: Context.close() frees its zkeys first
 
     def h_scalars(self, wtns):
         out = ctypes.create_string_buffer(self.domain_size * 32)
@@ -224,6 +228,7 @@ class ZKey:
         if self.handle:
             lib().b200_zkey_free(self.handle)
             self.handle = None
+            self.ctx._zkeys.discard(self)
 
     def __del__(self):
         try:
@@ -241,6 +246,7 @@ class Context:
         if rc != OK:
             raise B200Error(rc, lib().b200_last_error(None).decode())
         self.handle = h
+        self._zkeys = weakref.WeakSet()
 
     def _check(self, rc):
         if rc != OK:
@@ -248,6 +254,8 @@ class Context:
 
     def close(self):
         if self.handle:
+            for zk in list(self._zkeys):      # a zkey dereferences its context when freed (device, stream)
+                zk.free()
             lib().b200_free(self.handle)
             self.handle = None
 
@@ -321,6 +329,12 @@ class Context:
     # ---- instrumentation
     def launch_count(self):
         return int(lib().b200_launch_count(self.handle))
+
+    def timeline(self):
+        """[(phase name, start ms, end ms)] of the last call's timed segments (set_option("timeline", 1) first)."""
+        arr = (ctypes.c_float * 768)()
+        k = lib().b200_last_timeline(self.handle, arr, 768)
+        return [(lib().b200_phase_name(int(arr[3 * i])).decode(), float(arr[3 * i + 1]), float(arr[3 * i + 2])) for i in range(k)]
 
     def phase_ms(self):
         arr = (ctypes.c_float * 16)()

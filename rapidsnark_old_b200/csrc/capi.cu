@@ -36,6 +36,7 @@ int b200_init(int device, b200_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_h, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_xchg, cudaEventDisableTiming);
     for (int i = 0; i < Ctx::SORT_WS && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&h->c.ev_sort[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->c.ev_ws_acc[i], cudaEventDisableTiming);
@@ -91,6 +92,7 @@ void b200_free(b200_ctx *h) {
     for (int i = 0; i < 2; i++) { if (c->hstream_bc[i]) cudaStreamDestroy(c->hstream_bc[i]); if (c->ev_h_join[i]) cudaEventDestroy(c->ev_h_join[i]); }
     if (c->ev_h_fork) cudaEventDestroy(c->ev_h_fork);
     if (c->ev_h) cudaEventDestroy(c->ev_h);
+    if (c->ev_xchg) cudaEventDestroy(c->ev_xchg);
     cudaStreamDestroy(c->stream);
     delete h;
 }
@@ -113,6 +115,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;
     else if (!strcmp(name, "target_tasks_log2")) h->c.opt_target_tasks_log2 = value;
     else if (!strcmp(name, "max_batch_log2")) h->c.opt_max_batch_log2 = value;
+    else if (!strcmp(name, "timeline")) h->c.opt_timeline = value;
     else { h->c.err = std::string("unknown option ") + name; return B200_ERR_ARG; }
     return B200_OK;
 }
@@ -122,6 +125,13 @@ int b200_last_phase_ms(b200_ctx *h, float *out, int cap) {
     int k = cap < PH_COUNT ? cap : PH_COUNT;
     for (int i = 0; i < k; i++) out[i] = h->c.phase_ms[i];
     return k;
+}
+int b200_last_timeline(b200_ctx *h, float *out, int cap) {
+    if (!h || !out) return 0;
+    int k = (int)h->c.timeline.size();
+    if (k > cap) k = cap - cap % 3;
+    for (int i = 0; i < k; i++) out[i] = h->c.timeline[i];
+    return k / 3;
 }
 const char *b200_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? k_phase_names[i] : ""; }
 

@@ -12,6 +12,8 @@
 
 namespace b200 {
 
+static const u32 MSM_MAX_BATCH = 1u << 24;   // points per sort batch (entries < 2^32, entry index < 2^31)
+
 enum Phase {
     PH_H2D = 0,
     PH_MSM_SORT,       // digits + histogram + scan + scatter
@@ -35,6 +37,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t hstream = nullptr;    // H pipeline (a,b,c build + NTTs) overlapping the witness MSMs
     cudaEvent_t ev_h = nullptr;
+    cudaEvent_t ev_xchg = nullptr;     // in-process exchange: "my peer copies of the owners' polynomials are done"
+    bool attr_ntt = false, attr_acc_staged = false;   // cudaFuncSetAttribute is per DEVICE: remembered per context
     unsigned long long peer_enabled = 0;   // devices this ctx's device has been given peer access to
     int hi_prio = 0;                   // stream priority of the side / H streams
     cudaStream_t hstream_bc[2] = {nullptr, nullptr};   // b and c transform chains beside a's (opt_h_streams = 3)
@@ -61,6 +65,8 @@ struct Ctx {
     struct Seg { int ph, e0, e1; };
     std::vector<cudaEvent_t> evpool;   // phase timing events (reused call after call)
     std::vector<Seg> segs;
+    int opt_timeline = 0;              // 1: phase_collect also keeps (phase, start, end) of every segment, ms from the first
+    std::vector<float> timeline;       // triples, see b200_last_timeline
     int ev_used = 0;
     std::vector<DevBuf *> bufs;  // everything to free
 
@@ -158,15 +164,17 @@ inline void phase_begin(Ctx *ctx, Phase ph, cudaStream_t st = nullptr) {
 inline void phase_end(Ctx *ctx, cudaStream_t st = nullptr) { ctx->segs.back().e1 = phase_event(ctx, st ? st : ctx->stream); }
 inline void phase_collect(Ctx *ctx) {  // both streams must be synchronized
     static const bool timeline = getenv("B200_TIMELINE") != nullptr;
+    if (ctx->opt_timeline) ctx->timeline.clear();
     for (auto &s : ctx->segs) {
         if (s.e1 < 0) continue;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->evpool[s.e0], ctx->evpool[s.e1]) == cudaSuccess) ctx->phase_ms[s.ph] += ms;
-        if (timeline && !ctx->segs.empty()) {
+        if ((timeline || ctx->opt_timeline) && !ctx->segs.empty()) {
             float t0 = 0.f, t1 = 0.f;
             cudaEventElapsedTime(&t0, ctx->evpool[ctx->segs[0].e0], ctx->evpool[s.e0]);
             cudaEventElapsedTime(&t1, ctx->evpool[ctx->segs[0].e0], ctx->evpool[s.e1]);
-            fprintf(stderr, "[timeline] phase %d  %8.3f -> %8.3f ms\n", s.ph, t0, t1);
+            if (timeline) fprintf(stderr, "[timeline] phase %d  %8.3f -> %8.3f ms\n", s.ph, t0, t1);
+            if (ctx->opt_timeline) { ctx->timeline.push_back((float)s.ph); ctx->timeline.push_back(t0); ctx->timeline.push_back(t1); }
         }
     }
     ctx->segs.clear();

@@ -53,7 +53,6 @@ struct MsmGeom {
     u32 nplanes;    // ceil(log2(nseg)): bit planes of the segment index
 };
 
-static const u32 MSM_MAX_BATCH = 1u << 24;   // points per sort batch (entries < 2^32, entry index < 2^31)
 static const int MSM_MAX_WIN = 65;
 static const u32 MSM_TARGET_TASKS = 1u << 18;
 static const u32 MSM_WARM_MAX = 8;           // buckets cut into <= 8 tasks are folded by one thread (a serial chain), more by a
@@ -777,10 +776,9 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             if (ctx->opt_acc_smem == 2 && g2) {   // experimental: running sum + points staged in shared memory
                 kacc = k_msm_accumulate_staged<F, 3>;
                 smem = (size_t)128 * (sizeof(Pt) + 2 * sizeof(Affine<F>));
-                static bool attr_set = false;
-                if (!attr_set) {
+                if (!ctx->attr_acc_staged) {   // per device, hence per context
                     B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kacc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    attr_set = true;
+                    ctx->attr_acc_staged = true;
                 }
             } else if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
             else if (g2) { kacc = g2_minb == 3 ? k_msm_accumulate<F, false, 3> : k_msm_accumulate<F, false, 2>; }

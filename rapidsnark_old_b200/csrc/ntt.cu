@@ -326,12 +326,11 @@ static int ntt_launch_pass(Ctx *ctx, Fr *d_a, int k, const NttPass &ps, const Nt
     if (threads > 256) threads = 256;
     if (threads < 32) threads = 32;
     auto kern = k_ntt_pass<DIT, FUSE>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_ntt) {   // a function attribute belongs to the current device, not to the process
         B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
+        ctx->attr_ntt = true;
     }
     B200_LAUNCH(ctx, kern, grid, threads, smem, d_a, ps.lo, ps.S, ps.q, tb, k, n_inv);
     return B200_OK;

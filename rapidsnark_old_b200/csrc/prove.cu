@@ -285,7 +285,11 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         bool want = c->opt_precomp != 0 && pc >= 11 && pc <= 22 && rows <= 24 && need < (uint64_t)(free_b * 0.6) &&
-                    (uint64_t)rows * lenH < (1ull << 31) && (uint64_t)rows * lenA < (1ull << 31);
+                    (uint64_t)rows * lenH < (1ull << 31) && (uint64_t)rows * lenA < (1ull << 31) &&
+                    // a table MSM is a single sort batch (msm_enqueue_impl): longer shards keep the plain tables and
+                    // take the multi-batch path
+                    lenA <= MSM_MAX_BATCH && lenH <= MSM_MAX_BATCH &&
+                    !(c->opt_max_batch_log2 >= 4 && len_max > (1ull << c->opt_max_batch_log2));
         if (want) {
             auto build1 = [&](G1Affine **slice, uint64_t len, MsmTableRaw *t) -> int {
                 if (len == 0) return B200_OK;
@@ -386,8 +390,36 @@ int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_ou
 // the H stream.  Stage 2 (prove_stage2): combine, H MSM, collect.  A single GPU runs both back to back; with the
 // zkey sharded over several GPUs the caller exchanges the transformed polynomials between the stages (on the H
 // stream), each rank having run only the chains it owns.
+// After a failure part-way through a prove call work may still be queued on the main, H and side streams and result
+// slots stay marked used / busy: wait for everything and forget it, so that the next call starts from a clean state
+// instead of racing with stale kernels over d_wtns, d_a and the bucket buffers.
+static void prove_drain(Ctx *c) {
+    const std::string keep = c->err;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->hstream);
+    for (int i = 0; i < 2; i++) if (c->hstream_bc[i]) cudaStreamSynchronize(c->hstream_bc[i]);
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) {
+        if (c->side[i]) cudaStreamSynchronize(c->side[i]);
+        c->slot_info[i].used = false;
+        c->slot_busy[i] = false;
+    }
+    for (int w = 0; w < Ctx::SORT_WS; w++) { c->sort_readers[w] = 0; c->ws_acc_pending[w] = false; }
+    cudaGetLastError();
+    c->segs.clear();
+    c->ev_used = 0;
+    c->err = keep;
+}
+
+static int prove_stage1_impl(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, unsigned poly_mask, bool combine);
 static int prove_stage1(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, unsigned poly_mask, bool combine) {
     if (zk->stage1_done) { c->err = "prove_begin: the previous b200_prove_begin has not been finished"; return B200_ERR_ARG; }
+    int rc = prove_stage1_impl(c, zk, wtns, wtns_on_device, poly_mask, combine);
+    if (rc != B200_OK) prove_drain(c);
+    return rc;
+}
+
+static int prove_stage1_impl(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, unsigned poly_mask, bool combine) {
     cudaSetDevice(c->device);
     phase_reset(c);
     B200_TRY(wtns_upload(c, zk, wtns, wtns_on_device, poly_mask == 0 && !combine));
@@ -412,9 +444,16 @@ static int prove_stage1(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_de
     return B200_OK;
 }
 
+static int prove_stage2_impl(Ctx *c, b200_zkey *zk, void *out768);
 static int prove_stage2(Ctx *c, b200_zkey *zk, void *out768) {
     if (!zk->stage1_done) { c->err = "prove_finish without prove_begin"; return B200_ERR_ARG; }
     zk->stage1_done = false;
+    int rc = prove_stage2_impl(c, zk, out768);
+    if (rc != B200_OK) prove_drain(c);
+    return rc;
+}
+
+static int prove_stage2_impl(Ctx *c, b200_zkey *zk, void *out768) {
     cudaSetDevice(c->device);
     if (!zk->stage1_combined) {     // the exchanged a, b, c -> h, on the H stream behind the caller's exchange
         cudaStream_t main_stream = c->stream;
@@ -492,6 +531,22 @@ int b200_exchange_polys(b200_ctx *const *hs, b200_zkey *const *zks, int n) {
             // co->ev_h: recorded on the owner's H stream behind its transform chains (h_on_device)
             B200_CUDA_CHECK(cr, cudaStreamWaitEvent(cr->hstream, co->ev_h, 0));
             B200_CUDA_CHECK(cr, cudaMemcpyPeerAsync(dst, cr->device, src, co->device, bytes, cr->hstream));
+        }
+    }
+    // Write-after-read: the combine of b200_prove_finish overwrites d_a IN PLACE on the owner's H stream, while the
+    // peers' copies above read the owner's buffers on THEIR H streams.  Every receiver records "my copies are done"
+    // and every owner's H stream waits for all of them before anything later (the combine) may run.
+    if (n > 1) {
+        for (int r = 0; r < n; r++) {
+            Ctx *cr = &hs[r]->c;
+            cudaSetDevice(cr->device);
+            B200_CUDA_CHECK(cr, cudaEventRecord(cr->ev_xchg, cr->hstream));
+        }
+        for (int i = 0; i < 3 && i < n; i++) {   // owners are shards 0 .. min(3, n) - 1
+            Ctx *co = &hs[i]->c;
+            cudaSetDevice(co->device);
+            for (int r = 0; r < n; r++)
+                if (r != i) B200_CUDA_CHECK(co, cudaStreamWaitEvent(co->hstream, hs[r]->c.ev_xchg, 0));
         }
     }
     return B200_OK;

@@ -5,6 +5,7 @@
 #include <iostream>
 #include <stdexcept>
 #include <thread>
+#include "minijson.hpp"
 #include "wtns_utils.hpp"
 
 static std::string getfilename(std::string path) {
@@ -15,18 +16,7 @@ static std::string getfilename(std::string path) {
 
 static std::string jsonEscape(const std::string &s) {
     std::string o;
-    for (char ch : s) {
-        switch (ch) {
-            case '"': o += "\\\""; break;
-            case '\\': o += "\\\\"; break;
-            case '\n': o += "\\n"; break;
-            case '\r': o += "\\r"; break;
-            case '\t': o += "\\t"; break;
-            default:
-                if ((unsigned char)ch < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", ch); o += b; }
-                else o += ch;
-        }
-    }
+    minijson::escape(o, s);
     return o;
 }
 
@@ -88,8 +78,11 @@ void FullProver::thread_calculateProve() {
         if (it == circuits.end()) throw std::runtime_error("unknown circuit: " + circuit);
         Circuit &ck = it->second;
         {
+            // fullprover.cpp:108-113: the request body is parsed first (malformed input fails the request here, before
+            // the witness generator is spawned) and written back as nlohmann's compact dump
+            minijson::Value j = minijson::parse(executingInput);
             std::ofstream file("./build/input_" + circuit + ".json");
-            file << executingInput;
+            file << minijson::dump(j);
         }
         // witness generation by the circom-generated binary (process boundary, fullprover.cpp:117-132)
         std::string witnessFile("./build/" + circuit + ".wtns");
@@ -115,12 +108,13 @@ void FullProver::thread_calculateProve() {
         AltBn128::FrElement *wtnsData = (AltBn128::FrElement *)wtns->getSectionData(2);
         if (wtns->getSectionSize(2) < (uint64_t)ck.header->nVars * 32) throw std::runtime_error("witness too short for this zkey");
 
-        std::string pd = "[";
+        // a json that nothing was pushed to dumps as `null`, not `[]` (fullprover.cpp:145-150 with nPublic == 0)
+        std::string pd = ck.header->nPublic ? "[" : "null";
         for (uint32_t i = 1; i <= ck.header->nPublic; i++) {
             if (i > 1) pd += ",";
             pd += "\"" + AltBn128::le32ToString(&wtnsData[i]) + "\"";
         }
-        pd += "]";
+        if (ck.header->nPublic) pd += "]";
         pubData = pd;
 
         if (!isCanceled()) proof = ck.prover->prove(wtnsData)->toJson();

@@ -72,12 +72,13 @@ int main(int argc, char **argv) {
 
         std::ofstream publicFile;
         publicFile.open(publicFilename);
-        publicFile << "[";
+        // `json jsonPublic;` with nothing pushed streams as `null` (main_prover.cpp:85-93 with nPublic == 0)
+        publicFile << (zkeyHeader->nPublic ? "[" : "null");
         for (uint32_t i = 1; i <= zkeyHeader->nPublic; i++) {
             if (i > 1) publicFile << ",";
             publicFile << "\"" << AltBn128::le32ToString(&wtnsData[i]) << "\"";
         }
-        publicFile << "]";
+        if (zkeyHeader->nPublic) publicFile << "]";
         publicFile.close();
 
         if (const char *dump = getenv("B200_DUMP_MSMS")) {

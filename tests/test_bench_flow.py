@@ -63,6 +63,9 @@ class _FakeContext:
     def phase_ms(self):
         return {"msm_accumulate_g1": 4.0, "msm_accumulate_g2": 2.0}
 
+    def timeline(self):
+        return [("msm_sort", 0.0, 0.5), ("msm_accumulate_g2", 0.5, 2.5), ("ntt_h", 0.6, 2.0), ("msm_accumulate_g1", 2.5, 6.5)]
+
     def close(self):
         pass
 
@@ -102,6 +105,9 @@ def test_own_arm_flow_with_stand_ins(monkeypatch):
         assert key in line, key
     assert line["value"] == 5.0 and line["gpu_launches"] == 60 and line["higher_is_better"] is False
     assert line["e2e"]["h2d_bytes_per_step"] == (64 - 6) * 32 and line["e2e"]["d2h_bytes_per_step"] == 768
-    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source"}
+    assert line["roofline"]["traffic"] is None        # the committed capture is of 2^20, this run is 2^6
+    assert line["circom_like_witness"]["value"] == 3.3333 and line["e2e"]["pageable_host_witness_ms"] == 3.3333   # 10 ms / 3 steps
+    assert line["timeline_ms"]["_span"] == 6.5 and line["timeline_ms"]["ntt_h"]["busy"] == 1.4
     assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
     assert "workload" in line["config"]
