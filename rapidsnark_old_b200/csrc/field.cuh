@@ -26,6 +26,12 @@
 #ifndef B200_LAZY_PAIR
 #define B200_LAZY_PAIR 1
 #endif
+//   B200_FAST_SQR   1: squaring = 36 wide multiplies (off-diagonal products once, doubled) + a separate Montgomery
+//                      reduction (64) instead of the 128 of a general product: 2 of the 10 products of a G1 mixed
+//                      addition are squarings (montgomerybuilder.js:134-141)
+#ifndef B200_FAST_SQR
+#define B200_FAST_SQR 1
+#endif
 
 namespace b200 {
 
@@ -367,7 +373,66 @@ HD void sqr8(u32 *t, const u32 *a) {
 }
 #else
 HD void mul8x8(u32 *t, const u32 *a, const u32 *b) { mul_nxn<8>(t, a, b); }
+#if B200_FAST_SQR
+// t[0..15] = a^2 with 36 wide multiplies instead of 64: the 28 products a_i a_j (i < j) once, doubled, plus the 8
+// squares a_i^2 (the reference's generated squaring does the same on 4 x 64-bit limbs: montgomerybuilder.js:134-141).
+// Same even/odd accumulators as mul_nxn: a product a_i a_j sits at word position i + j; those with i + j even are
+// chained into E (E[k] = position k), the others into O (O[k] = position k + 1), so that within one row i the
+// products j = i+1, i+3, .. (and j = i+2, i+4, ..) are adjacent, non-overlapping 64-bit values of ONE carry chain.
+// The word above a chain's top only ever holds earlier end-of-chain carries (0, 1, 2), so one addc closes the chain.
+HD void sqr8(u32 *t, const u32 *a) {
+    u32 E[16], O[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        {   // j = i+1, i+3, ..: odd positions 2i+1, 2i+3, .. -> O[2i], O[2i+2], ..
+            const int s = 2 * i;
+            O[s] = mad_lo_cc(a[i], a[i + 1], O[s]);
+            O[s + 1] = madc_hi_cc(a[i], a[i + 1], O[s + 1]);
+            int k = s + 2;
+#pragma unroll
+            for (int j = i + 3; j < 8; j += 2, k += 2) {
+                O[k] = madc_lo_cc(a[i], a[j], O[k]);
+                O[k + 1] = madc_hi_cc(a[i], a[j], O[k + 1]);
+            }
+            if (k < 16) O[k] = addc(O[k], 0);
+        }
+        if (i + 2 < 8) {   // j = i+2, i+4, ..: even positions 2i+2, 2i+4, .. -> E[2i+2], ..
+            const int s = 2 * i + 2;
+            E[s] = mad_lo_cc(a[i], a[i + 2], E[s]);
+            E[s + 1] = madc_hi_cc(a[i], a[i + 2], E[s + 1]);
+            int k = s + 2;
+#pragma unroll
+            for (int j = i + 4; j < 8; j += 2, k += 2) {
+                E[k] = madc_lo_cc(a[i], a[j], E[k]);
+                E[k + 1] = madc_hi_cc(a[i], a[j], E[k + 1]);
+            }
+            if (k < 16) E[k] = addc(E[k], 0);
+        }
+    }
+    // off-diagonal sum = E + (O << 32); it is below 2^511, so doubling cannot overflow the 16 words
+    t[0] = E[0];
+    t[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 15; k++) t[k] = addc_cc(E[k], O[k - 1]);
+    t[15] = addc(E[15], O[14]);
+#pragma unroll
+    for (int k = 15; k > 0; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
+    t[0] <<= 1;
+    // + sum a_i^2 2^(64 i): one carry chain over all 16 words
+    t[0] = mad_lo_cc(a[0], a[0], t[0]);
+    t[1] = madc_hi_cc(a[0], a[0], t[1]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        t[2 * i] = madc_lo_cc(a[i], a[i], t[2 * i]);
+        if (i < 7) t[2 * i + 1] = madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+        else t[2 * i + 1] = madc_hi(a[i], a[i], t[2 * i + 1]);
+    }
+}
+#else
 HD void sqr8(u32 *t, const u32 *a) { mul_nxn<8>(t, a, a); }
+#endif
 #endif
 
 // t -= s over 16 limbs; when the difference is negative p * 2^256 is added back, so for |t - s| < p * 2^256 the
@@ -439,7 +504,7 @@ HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
 
 template <class P>
 HD Fp<P> fp_sqr(const Fp<P> &a) {
-#if B200_KARATSUBA
+#if B200_KARATSUBA || B200_FAST_SQR
     u32 t[16];
     detail::sqr8(t, a.v);
     Fp<P> r;

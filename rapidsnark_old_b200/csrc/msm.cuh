@@ -782,7 +782,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
                 }
             } else if (acc_smem) { kacc = g2 ? k_msm_accumulate<F, true, 3> : k_msm_accumulate<F, true, 4>; smem = acc_smem_bytes; }
             else if (g2) { kacc = g2_minb == 3 ? k_msm_accumulate<F, false, 3> : k_msm_accumulate<F, false, 2>; }
-            else { kacc = k_msm_accumulate<F, false, 3>; }   // 128 registers: four CTAs (16 warps) per SM
+            else { kacc = k_msm_accumulate<F, false, 4>; }   // capped at 128 registers: four CTAs (16 warps) per SM
             B200_LAUNCH(ctx, kacc, agrid, 128, smem, bs, d_entries, d_hist, d_tasks, d_plan + 2, g.CAP, d_hot_base, d_buckets, d_partial, add_existing);
         }
         phase_end(ctx);
