@@ -294,13 +294,19 @@ def run_own(args):
     dev = torch.device("cuda", local)
     spread_h = world > 1 and not args.replicate_h    # N > 1: a, b, c transform chains on different ranks + NCCL broadcasts
 
+    fused = world == 1 and not emu      # one GPU: b200_groth16_prove, the whole proof in one C call
+
     def step_resident():
+        if fused:
+            return zk.prove(wt_dev.data_ptr(), vk, r32, s32, on_device=True)
         prep = blind_prepare()
         if spread_h:
             return finish(bdist.prove_msms_distributed(zk, wt_dev.data_ptr(), True, s.n, dev), prep)
         return finish(zk.prove_msms_dev(wt_dev.data_ptr()), prep)
 
     def step_e2e():
+        if fused:
+            return zk.prove(wt_host.data_ptr(), vk, r32, s32)
         prep = blind_prepare()
         if spread_h:
             return finish(bdist.prove_msms_distributed(zk, wt_host.data_ptr(), False, s.n, dev), prep)
@@ -350,6 +356,8 @@ def run_own(args):
     wt_pageable_addr = ctypes.addressof(wt_pageable)
 
     def step_e2e_pageable():
+        if fused:
+            return zk.prove(wt_pageable_addr, vk, r32, s32)
         prep = blind_prepare()
         if spread_h:
             return finish(bdist.prove_msms_distributed(zk, wt_pageable_addr, False, s.n, dev), prep)
@@ -367,12 +375,16 @@ def run_own(args):
         cw_dev = cw_host.cuda()
 
         def step_circom_resident():
+            if fused:
+                return zk.prove(cw_dev.data_ptr(), vk, r32, s32, on_device=True)
             prep = blind_prepare()
             if spread_h:
                 return finish(bdist.prove_msms_distributed(zk, cw_dev.data_ptr(), True, s.n, dev), prep)
             return finish(zk.prove_msms_dev(cw_dev.data_ptr()), prep)
 
         def step_circom_e2e():
+            if fused:
+                return zk.prove(cw_host.data_ptr(), vk, r32, s32)
             prep = blind_prepare()
             if spread_h:
                 return finish(bdist.prove_msms_distributed(zk, cw_host.data_ptr(), False, s.n, dev), prep)

@@ -96,6 +96,12 @@ typedef struct b200_zkey_desc {
 
 int b200_zkey_upload(b200_ctx *ctx, const b200_zkey_desc *desc, b200_zkey **out);
 void b200_zkey_free(b200_zkey *zk);
+/* A second handle on the SAME resident tables for another context on the same device: the view owns only its
+ * per-proof buffers (witness, a, b, c), so two contexts - two host threads - can prove against one zkey at the same
+ * time and the GPU overlaps one proof's tail (last bucket reduction, result read-back, host finalisation) with the
+ * next proof's start: the reference's server use (src/fullprover.cpp:84-99) as a throughput mode.  Views and the
+ * source may be freed in any order; the tables go with the last of them. */
+int b200_zkey_share(b200_ctx *ctx, b200_zkey *src, b200_zkey **out);
 /* a, b, c -> h scalars of groth16.cpp:52-163 (normal form, domain_size x 32 B) to a host buffer */
 int b200_h_scalars(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *h_out_host);
 /* H pipeline + this shard's part of the five MSMs of groth16.cpp:165-207.
@@ -103,6 +109,21 @@ int b200_h_scalars(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *h_
 int b200_prove_msms(b200_ctx *ctx, b200_zkey *zk, const void *wtns_host, void *out768);
 /* same with the witness already in device memory (bench: inputs resident in HBM) */
 int b200_prove_msms_dev(b200_ctx *ctx, b200_zkey *zk, const void *d_wtns, void *out768);
+
+/* The whole proof in ONE call - Prover::prove, groth16.cpp:48-253: b200_prove_msms + blinding + to-affine, with the
+ * host-side blinding done while the GPU works and in the order the five results arrive (what is left after the last
+ * kernel is two group additions and one inversion).  r32, s32: the blinding factors (32-byte little-endian; the
+ * reference draws 31 random bytes each, groth16.cpp:213-217).  out_proof256 = A (G1 affine 64 B) | B (G2 affine 128 B)
+ * | C (G1 affine 64 B), Montgomery; out_msms768 (may be NULL) = the five pre-blinding points as b200_prove_msms.
+ * Single-GPU zkeys only (shard_count = 1). */
+typedef struct b200_vkey {
+    const void *alpha1, *beta1; /* G1 affine 64 B each (zkey header, zkey_utils.cpp:41-46) */
+    const void *beta2;          /* G2 affine 128 B */
+    const void *delta1;         /* G1 */
+    const void *delta2;         /* G2 */
+} b200_vkey;
+int b200_groth16_prove(b200_ctx *ctx, b200_zkey *zk, const void *wtns, int wtns_on_device, const b200_vkey *vk,
+                       const void *r32, const void *s32, void *out_proof256, void *out_msms768);
 
 /* Two-stage form of b200_prove_msms for zkeys sharded over several GPUs (one ctx per GPU, one process per GPU).
  * The H pipeline of groth16.cpp:101-163 is three independent transform chains (a, b, c) up to the final combine;

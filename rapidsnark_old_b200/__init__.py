@@ -30,8 +30,8 @@ EXPORTS = [
     "b200_last_timeline",
     "b200_msm_g1", "b200_msm_g2", "b200_msm_g1_dev", "b200_msm_g2_dev", "b200_set_msm_window", "b200_set_option",
     "b200_ntt_fr", "b200_ntt_fr_dev",
-    "b200_zkey_upload", "b200_zkey_free", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
-    "b200_prove_begin", "b200_prove_finish", "b200_exchange_polys",
+    "b200_zkey_upload", "b200_zkey_free", "b200_zkey_share", "b200_h_scalars", "b200_prove_msms", "b200_prove_msms_dev", "b200_stream",
+    "b200_prove_begin", "b200_prove_finish", "b200_exchange_polys", "b200_groth16_prove",
     "b200_groth16_finalize", "b200_groth16_blind_prepare", "b200_groth16_finalize_prepared", "b200_host_fold_partials",
     "b200_fq_to_decimal",
     "b200_fixed_base_g1", "b200_fixed_base_g2", "b200_synth_chain",
@@ -49,6 +49,10 @@ class B200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("b200snark error %d: %s" % (code, msg))
         self.code = code
+
+
+class VKey(ctypes.Structure):
+    _fields_ = [("alpha1", _vp), ("beta1", _vp), ("beta2", _vp), ("delta1", _vp), ("delta2", _vp)]
 
 
 class ZKeyDesc(ctypes.Structure):
@@ -83,11 +87,13 @@ def lib():
         L.b200_ntt_fr_dev.argtypes = [_vp, _vp, _u64, _int]
         L.b200_zkey_upload.argtypes = [_vp, ctypes.POINTER(ZKeyDesc), ctypes.POINTER(_vp)]
         L.b200_zkey_free.argtypes = [_vp]
+        L.b200_zkey_share.argtypes = [_vp, _vp, ctypes.POINTER(_vp)]
         L.b200_h_scalars.argtypes = [_vp, _vp, _vp, _vp]
         L.b200_prove_msms.argtypes = [_vp, _vp, _vp, _vp]
         L.b200_prove_msms_dev.argtypes = [_vp, _vp, _vp, _vp]
         L.b200_prove_begin.argtypes = [_vp, _vp, _vp, _int, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]
         L.b200_prove_finish.argtypes = [_vp, _vp, _vp]
+        L.b200_groth16_prove.argtypes = [_vp, _vp, _vp, _int, ctypes.POINTER(VKey), _vp, _vp, _vp, _vp]
         L.b200_exchange_polys.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _int]
         L.b200_stream.restype = _vp
         L.b200_stream.argtypes = [_vp]
@@ -209,6 +215,16 @@ class ZKey:
         self.ctx._check(lib().b200_prove_msms_dev(self.ctx.handle, self.handle, _vp(d_wtns), out))
         return out.raw
 
+    def prove(self, wtns, vk, r32, s32, on_device=False):
+        """The whole proof in one call (b200_groth16_prove): -> (msms768, proof256 = A | B | C affine Montgomery).
+        vk: dict with alpha1, beta1, beta2, delta1, delta2 (bytes)."""
+        key = VKey(_ptr(vk["alpha1"]), _ptr(vk["beta1"]), _ptr(vk["beta2"]), _ptr(vk["delta1"]), _ptr(vk["delta2"]))
+        proof, msms = ctypes.create_string_buffer(256), ctypes.create_string_buffer(768)
+        w = _vp(wtns) if on_device else _ptr(wtns)
+        self.ctx._check(lib().b200_groth16_prove(self.ctx.handle, self.handle, w, 1 if on_device else 0, ctypes.byref(key),
+                                                 _ptr(r32), _ptr(s32), proof, msms))
+        return msms.raw, proof.raw
+
     def prove_begin(self, wtns, on_device=False, poly_mask=7):
         """Stage 1 of the two-stage prove (multi-GPU): -> ([d_a, d_b, d_c] device addresses, H-stream handle).
         Returns without synchronising; exchange the buffers on that stream, then call prove_finish()."""
@@ -310,6 +326,12 @@ class Context:
         h = _vp()
         self._check(lib().b200_zkey_upload(self.handle, ctypes.byref(d), ctypes.byref(h)))
         return ZKey(self, h, (d, keep))
+
+    def zkey_share(self, zk):
+        """A view of `zk`'s resident tables for THIS context (same device): concurrent proofs against one zkey."""
+        h = _vp()
+        self._check(lib().b200_zkey_share(self.handle, zk.handle, ctypes.byref(h)))
+        return ZKey(self, h, zk._keep)
 
     # ---- synthetic tables
     def fixed_base_g1(self, base_affine, scalars32, n):

@@ -201,6 +201,12 @@ void ntt_free_tables(Ctx *ctx);   // ntt.cu
 // src/hostmath.cpp (g++): planes[set][0..nplanes-1] = bit-plane sums of S, planes[set][nplanes] = sum of W
 void host_msm_finish_g1(const void *planes, int nsets, int nplanes, int L, int nwin, int c, void *out);
 void host_msm_finish_g2(const void *planes, int nsets, int nplanes, int L, int nwin, int c, void *out);
+// src/hostmath.cpp: blinding of groth16.cpp:209-253 in pieces (see there)
+void groth16_blind_prepare(const void *delta1, const void *delta2, const uint8_t *r32, const uint8_t *s32, void *prep640);
+void groth16_blind_ab(const void *pi_a128, const void *pib1_128, const void *alpha1, const void *beta1, const void *prep640,
+                      const uint8_t *r32, const uint8_t *s32, void *outA64, void *outT128);
+void groth16_blind_b(const void *pi_b256, const void *beta2, const void *prep640, void *outB128);
+void groth16_blind_c(const void *pi_c128, const void *pih128, const void *T128, const void *prep640, void *outC64);
 
 // msm entry points implemented in msm_g1.cu / msm_g2.cu
 struct MsmTableRaw {        // resident per-window table 2^(c*j) * P_i (see msm.cuh); tbl == nullptr: none

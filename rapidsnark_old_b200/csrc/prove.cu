@@ -37,6 +37,10 @@ struct b200_zkey {
     G2Affine *d_B2 = nullptr;                                                   // per-window tables (t*.tbl)
     MsmTableRaw tA, tB1, tB2, tC, tH;
     Fr *d_wtns = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
+    // b200_zkey_share: a view borrows the parent's resident tables / CSR and owns only its per-proof buffers
+    b200_zkey *parent = nullptr;
+    int views = 0;          // live views of this (parent) zkey
+    bool released = false;  // b200_zkey_free was called on a parent that still has views: freed with the last view
 };
 
 static Range shard_range(uint64_t len, u32 idx, u32 cnt) {
@@ -182,14 +186,59 @@ int b200_ntt_fr(b200_ctx *h, void *a_host, uint64_t n, int inverse) {
 }
 
 // ---------------------------------------------------------------------------------------------- zkey
-void b200_zkey_free(b200_zkey *zk) {
-    if (!zk) return;
-    cudaSetDevice(zk->ctx->device);
-    cudaStreamSynchronize(zk->ctx->stream);
-    void *all[] = {zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->d_A, zk->d_B1, zk->d_C, zk->d_H,
-                   zk->d_B2, zk->d_wtns, zk->d_a, zk->d_b, zk->d_c};
+static void zkey_free_tables(b200_zkey *zk) {
+    void *all[] = {zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->d_A, zk->d_B1, zk->d_C, zk->d_H, zk->d_B2};
     for (void *p : all) if (p) cudaFree(p);
     delete zk;
+}
+
+void b200_zkey_free(b200_zkey *zk) {
+    if (!zk || zk->released) return;
+    cudaSetDevice(zk->ctx->device);
+    cudaStreamSynchronize(zk->ctx->stream);
+    void *work[] = {zk->d_wtns, zk->d_a, zk->d_b, zk->d_c};
+    for (void *p : work) if (p) cudaFree(p);
+    zk->d_wtns = zk->d_a = zk->d_b = zk->d_c = nullptr;
+    if (zk->parent) {                       // a view: give the tables back
+        b200_zkey *par = zk->parent;
+        delete zk;
+        if (--par->views == 0 && par->released) zkey_free_tables(par);
+        return;
+    }
+    if (zk->views > 0) { zk->released = true; return; }   // tables stay until the last view is gone
+    zkey_free_tables(zk);
+}
+
+int b200_zkey_share(b200_ctx *h, b200_zkey *src, b200_zkey **out) {
+    if (!h || !src || !out) return B200_ERR_ARG;
+    Ctx *c = &h->c;
+    *out = nullptr;
+    b200_zkey *root = src->parent ? src->parent : src;
+    if (root->released) { c->err = "zkey_share: the source zkey has been freed"; return B200_ERR_ARG; }
+    if (c->device != root->ctx->device) { c->err = "zkey_share: the view's context must be on the source's device"; return B200_ERR_ARG; }
+    cudaSetDevice(c->device);
+    b200_zkey *zk = new b200_zkey(*root);
+    zk->ctx = c;
+    zk->parent = root;
+    zk->views = 0;
+    zk->released = false;
+    zk->stage1_done = zk->stage1_combined = false;
+    zk->d_wtns = zk->d_a = zk->d_b = zk->d_c = nullptr;
+    const size_t n = root->domain_size;
+    cudaError_t e = cudaMalloc(&zk->d_wtns, (size_t)root->n_vars * sizeof(Fr));
+    if (e == cudaSuccess) e = cudaMalloc(&zk->d_a, n * sizeof(Fr));
+    if (e == cudaSuccess) e = cudaMalloc(&zk->d_b, n * sizeof(Fr));
+    if (e == cudaSuccess) e = cudaMalloc(&zk->d_c, n * sizeof(Fr));
+    if (e != cudaSuccess) {
+        c->err = std::string("zkey_share: ") + cudaGetErrorString(e);
+        void *work[] = {zk->d_wtns, zk->d_a, zk->d_b, zk->d_c};
+        for (void *p : work) if (p) cudaFree(p);
+        delete zk;
+        return B200_ERR_CUDA;
+    }
+    root->views++;
+    *out = zk;
+    return B200_OK;
 }
 
 int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
@@ -453,7 +502,8 @@ static int prove_stage2(Ctx *c, b200_zkey *zk, void *out768) {
     return rc;
 }
 
-static int prove_stage2_impl(Ctx *c, b200_zkey *zk, void *out768) {
+// combine (when not done in stage 1) + the H MSM, all enqueued, nothing waited for
+static int prove_enqueue_h(Ctx *c, b200_zkey *zk) {
     cudaSetDevice(c->device);
     if (!zk->stage1_combined) {     // the exchanged a, b, c -> h, on the H stream behind the caller's exchange
         cudaStream_t main_stream = c->stream;
@@ -464,22 +514,31 @@ static int prove_stage2_impl(Ctx *c, b200_zkey *zk, void *out768) {
         c->stream = main_stream;
         B200_TRY(rc);
     }
+    // the digit sort of h runs on the H-pipeline stream right behind the NTTs (own sort workspace), i.e. under the
+    // witness accumulations; only the H accumulation itself waits for it on the main stream
+    return msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true,
+                          1, c->hstream);
+}
+
+static int prove_sync_all(Ctx *c) {
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) B200_CUDA_CHECK(c, cudaStreamSynchronize(c->side[i]));
+    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->hstream));
+    phase_collect(c);
+    return B200_OK;
+}
+
+static int prove_stage2_impl(Ctx *c, b200_zkey *zk, void *out768) {
+    B200_TRY(prove_enqueue_h(c, zk));
     uint8_t *o = (uint8_t *)out768;
     G1Xyzz pih, pia, pib1, pic;
     G2Xyzz pib;
-    // the digit sort of h runs on the H-pipeline stream right behind the NTTs (own sort workspace), i.e. under the
-    // witness accumulations; only the H accumulation itself waits for it on the main stream
-    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true,
-                            1, c->hstream));
     B200_TRY(msm_g1_collect(c, 0, &pih));
     B200_TRY(msm_g2_collect(c, 1, &pib));
     B200_TRY(msm_g1_collect(c, 2, &pia));
     B200_TRY(msm_g1_collect(c, 3, &pib1));
     B200_TRY(msm_g1_collect(c, 4, &pic));
-    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) B200_CUDA_CHECK(c, cudaStreamSynchronize(c->side[i]));
-    B200_CUDA_CHECK(c, cudaStreamSynchronize(c->hstream));
-    phase_collect(c);
+    B200_TRY(prove_sync_all(c));
     memcpy(o, &pih, 128);
     memcpy(o + 128, &pia, 128);
     memcpy(o + 256, &pib1, 128);
@@ -493,6 +552,48 @@ static int prove_msms_impl(b200_ctx *h, b200_zkey *zk, const void *wtns_host, bo
     Ctx *c = &h->c;
     B200_TRY(prove_stage1(c, zk, wtns_host, wtns_on_device, 7u, true));
     return prove_stage2(c, zk, out768);
+}
+
+// The whole of Prover::prove (groth16.cpp:48-253) in one call: everything is enqueued first, then the host does the
+// blinding work in the order the results become available - the key-only part (r*delta1, s*delta1, rs*delta1,
+// s*delta2: most of it) right away, s*A + r*B1 as soon as pi_a and pib1 are collected (the GPU is still busy with the
+// C and H accumulations then), B when the G2 reduction is through, and only C = ... + pih after the last kernel.
+static int groth16_prove_impl(Ctx *c, b200_zkey *zk, const void *wtns, bool on_device, const b200_vkey *vk, const uint8_t *r32,
+                              const uint8_t *s32, uint8_t *proof256, uint8_t *msms768) {
+    if (zk->stage1_done) { c->err = "groth16_prove: a b200_prove_begin is pending on this zkey"; return B200_ERR_ARG; }
+    B200_TRY(prove_stage1_impl(c, zk, wtns, on_device, 7u, true));
+    zk->stage1_done = false;
+    B200_TRY(prove_enqueue_h(c, zk));
+    uint8_t prep[640], T[128];
+    groth16_blind_prepare(vk->delta1, vk->delta2, r32, s32, prep);
+    G1Xyzz pih, pia, pib1, pic;
+    G2Xyzz pib;
+    B200_TRY(msm_g1_collect(c, 2, &pia));
+    B200_TRY(msm_g1_collect(c, 3, &pib1));
+    groth16_blind_ab(&pia, &pib1, vk->alpha1, vk->beta1, prep, r32, s32, proof256, T);
+    B200_TRY(msm_g2_collect(c, 1, &pib));
+    groth16_blind_b(&pib, vk->beta2, prep, proof256 + 64);
+    B200_TRY(msm_g1_collect(c, 4, &pic));
+    B200_TRY(msm_g1_collect(c, 0, &pih));
+    groth16_blind_c(&pic, &pih, T, prep, proof256 + 192);
+    B200_TRY(prove_sync_all(c));
+    if (msms768) {
+        memcpy(msms768, &pih, 128); memcpy(msms768 + 128, &pia, 128); memcpy(msms768 + 256, &pib1, 128);
+        memcpy(msms768 + 384, &pib, 256); memcpy(msms768 + 640, &pic, 128);
+    }
+    return B200_OK;
+}
+
+int b200_groth16_prove(b200_ctx *h, b200_zkey *zk, const void *wtns, int wtns_on_device, const b200_vkey *vk, const void *r32,
+                       const void *s32, void *out_proof256, void *out_msms768) {
+    if (!h || !zk || !wtns || !vk || !r32 || !s32 || !out_proof256) return B200_ERR_ARG;
+    if (!vk->alpha1 || !vk->beta1 || !vk->beta2 || !vk->delta1 || !vk->delta2) { h->c.err = "groth16_prove: null key point"; return B200_ERR_ARG; }
+    if (zk->sharded) { h->c.err = "groth16_prove: the zkey is one shard of several (use b200_prove_msms + fold + finalize)"; return B200_ERR_ARG; }
+    Ctx *c = &h->c;
+    int rc = groth16_prove_impl(c, zk, wtns, wtns_on_device != 0, vk, (const uint8_t *)r32, (const uint8_t *)s32,
+                                (uint8_t *)out_proof256, (uint8_t *)out_msms768);
+    if (rc != B200_OK) prove_drain(c);
+    return rc;
 }
 
 int b200_prove_begin(b200_ctx *h, b200_zkey *zk, const void *wtns, int wtns_on_device, uint32_t poly_mask,

@@ -124,12 +124,27 @@ std::unique_ptr<Proof<Engine>> Prover<Engine>::prove(typename Engine::FrElement 
     } else {
         if (getrandom(r, 31, 0) != 31 || getrandom(s, 31, 0) != 31) throw std::runtime_error("getrandom failed");
     }
+    if (G == 1) {
+        // one GPU: the fused call does the blinding on this thread while the GPU works, in the order the five
+        // results arrive (include/b200snark.h b200_groth16_prove)
+        b200_vkey vk{&vk_alpha1, &vk_beta1, &vk_beta2, &vk_delta1, &vk_delta2};
+        uint8_t out[256];
+        if (b200_groth16_prove(gpus[0].ctx, gpus[0].zk, wtns, 0, &vk, r, s, out, lastMsms) != B200_OK)
+            throwCtx(gpus[0].ctx, "b200_groth16_prove");
+        lastPhases.clear();
+        float ms[16];
+        int k = b200_last_phase_ms(gpus[0].ctx, ms, 16);
+        for (int i = 0; i < k; i++) lastPhases.emplace_back(b200_phase_name(i), ms[i]);
+        std::unique_ptr<Proof<Engine>> p(new Proof<Engine>());
+        memcpy(&p->A, out, 64);
+        memcpy(&p->B, out + 64, 128);
+        memcpy(&p->C, out + 192, 64);
+        return p;
+    }
     uint8_t prep[640];
     std::thread blind([&]() { b200_groth16_blind_prepare(&vk_delta1, &vk_delta2, r, s, prep); });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joinBlind{blind};
-    if (G == 1) {
-        rcs[0] = b200_prove_msms(gpus[0].ctx, gpus[0].zk, wtns, parts.data());
-    } else if (getenv("B200_REPLICATE_H")) {     // every GPU repeats the whole H pipeline (A/B, no exchange)
+    if (getenv("B200_REPLICATE_H")) {     // every GPU repeats the whole H pipeline (A/B, no exchange)
         std::vector<std::thread> th;
         for (size_t g = 0; g < G; g++)
             th.emplace_back([&, g]() { rcs[g] = b200_prove_msms(gpus[g].ctx, gpus[g].zk, wtns, parts.data() + 768 * g); });

@@ -65,34 +65,61 @@ void groth16_blind_prepare(const void *delta1, const void *delta2, const uint8_t
     memcpy(o, &rd1, 128); memcpy(o + 128, &sd1, 128); memcpy(o + 256, &rsd1, 128); memcpy(o + 384, &sd2, 256);
 }
 
-void groth16_finalize_prepared(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
-                               const void *prep640, const uint8_t *r32, const uint8_t *s32, void *out256) {
-    const uint8_t *m = (const uint8_t *)msms768, *pp = (const uint8_t *)prep640;
-    HG1 pih, pi_a, pib1, pi_c, rd1, sd1, rsd1;
-    HG2 pi_b, sd2;
-    memcpy(&pih, m, 128); memcpy(&pi_a, m + 128, 128); memcpy(&pib1, m + 256, 128);
-    memcpy(&pi_b, m + 384, 256); memcpy(&pi_c, m + 640, 128);
-    memcpy(&rd1, pp, 128); memcpy(&sd1, pp + 128, 128); memcpy(&rsd1, pp + 256, 128); memcpy(&sd2, pp + 384, 256);
+// The finish in three pieces, each needing only some of the MSM results, so that a caller can run them as the
+// results arrive (b200_groth16_prove: pi_a and pib1 are ready long before pi_c and pih):
+//   blind_ab : A = affine(pi_a + alpha1 + r*delta1), B1 = affine(pib1 + beta1 + s*delta1), T = s*A + r*B1
+//   blind_b  : B = affine(pi_b + beta2 + s*delta2)
+//   blind_c  : C = affine(pi_c + pih + T - (rs)*delta1)
+void groth16_blind_ab(const void *pi_a128, const void *pib1_128, const void *alpha1, const void *beta1, const void *prep640,
+                      const uint8_t *r32, const uint8_t *s32, void *outA64, void *outT128) {
+    const uint8_t *pp = (const uint8_t *)prep640;
+    HG1 pi_a, pib1, rd1, sd1;
+    memcpy(&pi_a, pi_a128, 128); memcpy(&pib1, pib1_128, 128);
+    memcpy(&rd1, pp, 128); memcpy(&sd1, pp + 128, 128);
     HG1Affine a1, b1;
-    HG2Affine b2;
-    memcpy(&a1, alpha1, 64); memcpy(&b1, beta1, 64); memcpy(&b2, beta2, 128);
-
+    memcpy(&a1, alpha1, 64); memcpy(&b1, beta1, 64);
     ec_madd(pi_a, a1);                                   // pi_a += alpha1 + r*delta1      (:222-224)
     ec_add(pi_a, rd1);
-    ec_madd(pi_b, b2);                                   // pi_b += beta2 + s*delta2       (:226-228)
-    ec_add(pi_b, sd2);
     ec_madd(pib1, b1);                                   // pib1 += beta1 + s*delta1       (:230-232)
     ec_add(pib1, sd1);
-    ec_add(pi_c, pih);                                   // pi_c += pih                    (:234)
     HG1Affine pa = ec_to_affine(pi_a), pb1 = ec_to_affine(pib1);
-    ec_add(pi_c, scalar_mul(pa, s32, 32));               // + s*pi_a                       (:236-237)
-    ec_add(pi_c, scalar_mul(pb1, r32, 32));              // + r*pib1                       (:239-240)
-    ec_add(pi_c, ec_neg(rsd1));                          // - (rs)*delta1                  (:245-246)
+    HG1 t = scalar_mul(pa, s32, 32);                     // s*pi_a                         (:236-237)
+    ec_add(t, scalar_mul(pb1, r32, 32));                 // + r*pib1                       (:239-240)
+    memcpy(outA64, &pa, 64);
+    memcpy(outT128, &t, 128);
+}
 
+void groth16_blind_b(const void *pi_b256, const void *beta2, const void *prep640, void *outB128) {
+    HG2 pi_b, sd2;
+    memcpy(&pi_b, pi_b256, 256);
+    memcpy(&sd2, (const uint8_t *)prep640 + 384, 256);
+    HG2Affine b2;
+    memcpy(&b2, beta2, 128);
+    ec_madd(pi_b, b2);                                   // pi_b += beta2 + s*delta2       (:226-228)
+    ec_add(pi_b, sd2);
     HG2Affine B = ec_to_affine(pi_b);
+    memcpy(outB128, &B, 128);
+}
+
+void groth16_blind_c(const void *pi_c128, const void *pih128, const void *T128, const void *prep640, void *outC64) {
+    HG1 pi_c, pih, t, rsd1;
+    memcpy(&pi_c, pi_c128, 128); memcpy(&pih, pih128, 128); memcpy(&t, T128, 128);
+    memcpy(&rsd1, (const uint8_t *)prep640 + 256, 128);
+    ec_add(pi_c, pih);                                   // pi_c += pih                    (:234)
+    ec_add(pi_c, t);                                     // + s*pi_a + r*pib1              (:236-240)
+    ec_add(pi_c, ec_neg(rsd1));                          // - (rs)*delta1                  (:245-246)
     HG1Affine C = ec_to_affine(pi_c);
+    memcpy(outC64, &C, 64);
+}
+
+void groth16_finalize_prepared(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,
+                               const void *prep640, const uint8_t *r32, const uint8_t *s32, void *out256) {
+    const uint8_t *m = (const uint8_t *)msms768;
     uint8_t *o = (uint8_t *)out256;
-    memcpy(o, &pa, 64); memcpy(o + 64, &B, 128); memcpy(o + 192, &C, 64);
+    uint8_t T[128];
+    groth16_blind_ab(m + 128, m + 256, alpha1, beta1, prep640, r32, s32, o, T);
+    groth16_blind_b(m + 384, beta2, prep640, o + 64);
+    groth16_blind_c(m + 640, m, T, prep640, o + 192);
 }
 
 void groth16_finalize(const void *msms768, const void *alpha1, const void *beta1, const void *beta2,

@@ -300,6 +300,64 @@ def test_two_stage_prove_equals_one_call(ctx, orc):
     zk.free()
 
 
+@pytest.mark.parametrize("log_n", [6, 12])
+def test_fused_prove_is_msms_plus_reference_blinding(ctx, orc, log_n):
+    """b200_groth16_prove (one call, blinding interleaved with the collection of the results) = b200_prove_msms followed
+    by the reference's blinding (groth16.cpp:209-253, oracle) for the same r, s; also from a device-resident witness."""
+    import hashlib
+    import torch
+    s = synth_util.make(log_n)
+    wt = s.wtns_bytes()
+    r32 = hashlib.sha256(b"r%d" % log_n).digest()[:31] + b"\0"
+    s32 = hashlib.sha256(b"s%d" % log_n).digest()[:31] + b"\0"
+    zk = _upload(ctx, s)
+    msms, proof = zk.prove(wt, s.vk, r32, s32)
+    vk = s.vk
+    assert orc.msms_to_affine(msms) == synth_util.expected_affine(orc, s)
+    want = orc.blind(msms, vk["alpha1"], vk["beta1"], vk["beta2"], vk["delta1"], vk["delta2"], r32, s32)
+    assert proof == want
+    d_wt = torch.frombuffer(bytearray(wt), dtype=torch.uint8).cuda()
+    msms2, proof2 = zk.prove(d_wt.data_ptr(), s.vk, r32, s32, on_device=True)
+    assert proof2 == want and orc.msms_to_affine(msms2) == orc.msms_to_affine(msms)
+    assert orc.msms_to_affine(zk.prove_msms(wt)) == orc.msms_to_affine(msms)      # the plain call still works afterwards
+    zk.free()
+    zk2 = _upload(ctx, s, 0, 2)
+    with pytest.raises(b200.B200Error):
+        zk2.prove(wt, s.vk, r32, s32)              # one shard of two: no single-call proof
+    zk2.free()
+
+
+def test_zkey_views_prove_concurrently(ctx, orc):
+    """b200_zkey_share: three contexts (three host threads) prove against ONE resident zkey at the same time; every
+    proof equals the single-context one.  The source may be freed before its views."""
+    import hashlib
+    import threading
+    s = synth_util.make(12)
+    wt = s.wtns_bytes()
+    r32, s32 = hashlib.sha256(b"vr").digest()[:31] + b"\0", hashlib.sha256(b"vs").digest()[:31] + b"\0"
+    zk = _upload(ctx, s)
+    _, want = zk.prove(wt, s.vk, r32, s32)
+    others = [b200.Context(0) for _ in range(2)]
+    views = [c.zkey_share(zk) for c in others]
+    got = {}
+
+    def work(i, z):
+        got[i] = [z.prove(wt, s.vk, r32, s32)[1] for _ in range(4)]
+    th = [threading.Thread(target=work, args=(i, z)) for i, z in enumerate([zk] + views)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert all(p == want for i in range(3) for p in got[i])
+    zk.free()                                   # the tables stay until the last view goes
+    assert views[0].prove(wt, s.vk, r32, s32)[1] == want
+    with pytest.raises(b200.B200Error):
+        others[1].zkey_share(zk)                # freed source
+    for z, c in zip(views, others):
+        z.free()
+        c.close()
+
+
 @pytest.mark.parametrize("shards", [2, 3, 5])
 def test_h_pipeline_spread_over_ranks(orc, shards):
     """The N > 1 flow of dist.prove_msms_distributed on ONE device: every rank is its own context with its own
