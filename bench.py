@@ -84,7 +84,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def build_inputs(log_n, seed, g1_many, g2_many, fast=True, shard=None):
+def build_inputs(log_n, seed, g1_many, g2_many, fast=True, shard=None, bounds=None):
     """The synthetic circuit of SURVEY.md Appendix C.  fast: scalars from the library's host routine (FastSynth,
     identical values, seconds instead of minutes at 2^24); the point makers must then accept packed bytes.
     shard = (rank, world): only this rank's slices of the point tables are generated (s.shard_points)."""
@@ -94,7 +94,7 @@ def build_inputs(log_n, seed, g1_many, g2_many, fast=True, shard=None):
     log("[bench] synthetic circuit 2^%d: scalars in %.1fs" % (log_n, time.time() - t))
     t = time.time()
     if shard:
-        s.build_shard_points(g1_many, g2_many, *shard)
+        s.build_shard_points(g1_many, g2_many, *shard, bounds=bounds)
     else:
         s.build_points(g1_many, g2_many)
     log("[bench] point tables in %.1fs" % (time.time() - t))
@@ -257,7 +257,11 @@ def run_own(args):
     log_n = args.log_n
     # big circuits on several GPUs: every rank generates only the table slices it uploads (2^26: 24 GB of tables)
     shard_inputs = world > 1 and (args.shard_inputs or log_n >= 23)
-    s = build_inputs(log_n, 2, *gpu_point_makers(ctx), shard=(rank, world) if shard_inputs else None)
+    from rapidsnark_old_b200 import dist as bdist
+    # N > 1: ranks that run a transform chain of the H pipeline own a smaller point range (dist.shard_plan)
+    plan = bdist.shard_plan(world) if not args.even_shards else [(bdist.PLAN_DEN * r // world, bdist.PLAN_DEN * (r + 1) // world) for r in range(world)]
+    bounds = plan[rank] + (bdist.PLAN_DEN,)
+    s = build_inputs(log_n, 2, *gpu_point_makers(ctx), shard=(rank, world) if shard_inputs else None, bounds=bounds)
     if shard_inputs:
         p = {k: s.shard_table_address(k) for k in ("A", "B1", "B2", "C", "H")}
     else:
@@ -267,8 +271,14 @@ def run_own(args):
     for kv in args.opt:                                  # result unchecked); never used for a reported line
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
+    if emu:   # rank --emulate-rank of `emu`, with that world's plan
+        er = args.emulate_rank
+        eplan = bdist.shard_plan(emu) if not args.even_shards else [(bdist.PLAN_DEN * r // emu, bdist.PLAN_DEN * (r + 1) // emu) for r in range(emu)]
+        bounds = eplan[er] + (bdist.PLAN_DEN,)
+        if args.emulate_poly_mask == -2:
+            args.emulate_poly_mask = bdist.poly_mask(er, emu)
     zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"],
-                         p["H"], 0 if emu else rank, emu if emu else world)
+                         p["H"], args.emulate_rank if emu else rank, emu if emu else world, shard_bounds=bounds if (world > 1 or emu) else None)
     wt_bytes = s.wtns_bytes()
     # witness: pinned host copy (e2e) and device copy (value)
     wt_host = torch.empty(len(wt_bytes), dtype=torch.uint8).pin_memory()
@@ -276,8 +286,6 @@ def run_own(args):
     wt_dev = wt_host.cuda()
     r32, s32 = blinding_factors()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-
-    from rapidsnark_old_b200 import dist as bdist
 
     from concurrent.futures import ThreadPoolExecutor
     host_pool = ThreadPoolExecutor(max_workers=1)
@@ -296,20 +304,31 @@ def run_own(args):
 
     fused = world == 1 and not emu      # one GPU: b200_groth16_prove, the whole proof in one C call
 
+    def emu_spread(ptr, on_device):
+        # tuning aid: rank 0 of `emu` shards with only the transform chains in --emulate-poly-mask run here and no
+        # exchange (the other polynomials are whatever the buffers hold: the result is meaningless and unchecked)
+        prep = blind_prepare()
+        zk.prove_begin(ptr, on_device, args.emulate_poly_mask)
+        return finish(zk.prove_finish(), prep)
+
     def step_resident():
+        if emu and args.emulate_poly_mask >= 0:
+            return emu_spread(wt_dev.data_ptr(), True)
         if fused:
             return zk.prove(wt_dev.data_ptr(), vk, r32, s32, on_device=True)
         prep = blind_prepare()
         if spread_h:
-            return finish(bdist.prove_msms_distributed(zk, wt_dev.data_ptr(), True, s.n, dev), prep)
+            return finish(bdist.prove_msms_distributed(zk, wt_dev.data_ptr(), True, s.n, dev, plan=plan), prep)
         return finish(zk.prove_msms_dev(wt_dev.data_ptr()), prep)
 
     def step_e2e():
+        if emu and args.emulate_poly_mask >= 0:
+            return emu_spread(wt_host.data_ptr(), False)
         if fused:
             return zk.prove(wt_host.data_ptr(), vk, r32, s32)
         prep = blind_prepare()
         if spread_h:
-            return finish(bdist.prove_msms_distributed(zk, wt_host.data_ptr(), False, s.n, dev), prep)
+            return finish(bdist.prove_msms_distributed(zk, wt_host.data_ptr(), False, s.n, dev, plan=plan), prep)
         return finish(zk.prove_msms(wt_host.data_ptr()), prep)
 
     def barrier():
@@ -360,7 +379,7 @@ def run_own(args):
             return zk.prove(wt_pageable_addr, vk, r32, s32)
         prep = blind_prepare()
         if spread_h:
-            return finish(bdist.prove_msms_distributed(zk, wt_pageable_addr, False, s.n, dev), prep)
+            return finish(bdist.prove_msms_distributed(zk, wt_pageable_addr, False, s.n, dev, plan=plan), prep)
         return finish(zk.prove_msms(wt_pageable_addr), prep)
 
     ms_pageable, _, _ = timed(step_e2e_pageable, extra_steps, 3)
@@ -379,7 +398,7 @@ def run_own(args):
                 return zk.prove(cw_dev.data_ptr(), vk, r32, s32, on_device=True)
             prep = blind_prepare()
             if spread_h:
-                return finish(bdist.prove_msms_distributed(zk, cw_dev.data_ptr(), True, s.n, dev), prep)
+                return finish(bdist.prove_msms_distributed(zk, cw_dev.data_ptr(), True, s.n, dev, plan=plan), prep)
             return finish(zk.prove_msms_dev(cw_dev.data_ptr()), prep)
 
         def step_circom_e2e():
@@ -387,7 +406,7 @@ def run_own(args):
                 return zk.prove(cw_host.data_ptr(), vk, r32, s32)
             prep = blind_prepare()
             if spread_h:
-                return finish(bdist.prove_msms_distributed(zk, cw_host.data_ptr(), False, s.n, dev), prep)
+                return finish(bdist.prove_msms_distributed(zk, cw_host.data_ptr(), False, s.n, dev, plan=plan), prep)
             return finish(zk.prove_msms(cw_host.data_ptr()), prep)
 
         cm, _ = step_circom_e2e()
@@ -405,15 +424,19 @@ def run_own(args):
 
     pk, pk_kind = peaks()
     # dominant kernel: k_msm_accumulate<Fq> - 4 launches per proof (H, A, B1, C); algorithmic bytes 96 B/point
-    n_pts = [(zk_len(s.n, rank, world)), zk_len(s.n_vars, rank, world), zk_len(s.n_vars, rank, world),
-             zk_len(s.n_vars - s.n_public - 1, rank, world)]
-    alg_bytes = 96.0 * sum(n_pts) / 4
-    acc_ms = ph_res.get("msm_accumulate_g1", 0.0) / 4
+    zl = lambda total: total * bounds[1] // bounds[2] - total * bounds[0] // bounds[2]     # this rank's share
+    n_pts = [zl(s.n), zl(s.n_vars), zl(s.n_vars), zl(s.n_vars - s.n_public - 1)]
+    # launches of the G1 accumulation kernel per proof: one fused launch for all four MSMs on a single GPU, two
+    # (witness MSMs, then H) on sharded zkeys - counted from the timeline's segments
+    tls = timeline_summary(tl)
+    acc_launches = max(1, int(tls.get("msm_accumulate_g1", {}).get("segments", 4)))
+    alg_bytes = 96.0 * sum(n_pts) / acc_launches
+    acc_ms = ph_res.get("msm_accumulate_g1", 0.0) / acc_launches
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
     traffic, traffic_src = ncu_traffic(log_n, world)
-    roof = {"bound": "hbm", "kernel": "k_msm_accumulate<Fq>", "achieved": round(achieved, 2), "peak": pk["hbm_gbs"],
+    roof = {"bound": "hbm", "kernel": "k_msm_accumulate_sets<Fq> (G1 bucket accumulation)", "achieved": round(achieved, 2), "peak": pk["hbm_gbs"],
             "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 5), "traffic": traffic, "traffic_source": traffic_src,
-            "peak_kind": pk_kind,
+            "peak_kind": pk_kind, "launches_per_proof": acc_launches,
             "launch_ms": round(acc_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
             "note": "integer-ALU bound by construction (SURVEY 8d): ~10 Montgomery products of 8x8 32-bit limbs per "
                     "96 algorithmic bytes; see DESIGN.md for the IMAD roofline"}
@@ -423,9 +446,11 @@ def run_own(args):
             "vs_baseline": None, "dtype": "u256-mont", "data": "synthetic",
             "config": {"workload": "groth16 prove, BN254, 2^%d constraints, synthetic chain circuit" % log_n,
                        "n_vars": s.n_vars, "n_public": s.n_public, "n_coefs": s.n_coefs,
-                       "parallelism": ("point-range shards x%d, 1 NCCL all_gather of 768 B partials" % world) +
-                                      (", H transform chains a/b/c on ranks %s + 3 NCCL broadcasts of %d MB" %
-                                       (bdist.poly_owners(world), s.n * 32 >> 20) if spread_h else ""),
+                       "parallelism": ("point-range shards x%d (shares %s), 1 NCCL all_gather of 768 B partials" %
+                                       (world, [round((b - a) / bdist.PLAN_DEN, 4) for a, b in plan])) +
+                                      (", H transform chains a/b/c on ranks %s, every rank receives its slice of each "
+                                       "(NCCL send/recv, %d KB per slice)" %
+                                       (bdist.poly_owners(world), (s.n * 32 // world) >> 10) if spread_h else ""),
                        "l2": "inputs larger than L2 (0.5 GB of tables and coefficients per proof)"},
             "e2e": {"value": round(ms_e2e, 4), "unit": UNIT, "h2d_bytes_per_step": len(wt_bytes), "d2h_bytes_per_step": 768,
                     "pageable_host_witness_ms": round(ms_pageable, 4)},
@@ -435,7 +460,7 @@ def run_own(args):
             # the timeline below is the schedule of one proof
             "phase_stream_ms": {k: round(v, 4) for k, v in ph_res.items()},
             "phase_stream_ms_e2e": {k: round(v, 4) for k, v in ph_e2e.items()},
-            "timeline_ms": timeline_summary(tl)}
+            "timeline_ms": tls}
     if emu:
         line["config"]["emulated_shards"] = emu
         line["metric"] += "_EMULATED_RANK0_OF_%d" % emu
@@ -596,8 +621,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-inputs", action="store_true",
                     help="N > 1: generate only this rank's slices of the point tables (automatic from 2^23)")
+    ap.add_argument("--even-shards", action="store_true", help="N > 1: equal point ranges on every rank (A/B)")
     ap.add_argument("--replicate-h", action="store_true", help="N > 1: every rank runs the whole H pipeline (A/B)")
     ap.add_argument("--emulate-shards", type=int, default=0, help="tuning only: time rank 0 of K shards on one GPU")
+    ap.add_argument("--emulate-rank", type=int, default=0, help="tuning only, with --emulate-shards: which rank to play")
+    ap.add_argument("--emulate-poly-mask", type=int, default=-1,
+                    help="tuning only, with --emulate-shards: run only these transform chains (bit 0 a, 1 b, 2 c; -2 = the "
+                         "emulated rank's own), no exchange")
     ap.add_argument("--opt", nargs="*", default=[], help="tuning only: library options name=value (b200_set_option)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":

@@ -72,7 +72,8 @@ void b200_set_msm_window(b200_ctx *ctx, int c_bits);
  * 2 G2 only: running sum and cp.async-staged points in shared memory),
  * "precomp" (-1 auto / 0 off / 1 on: per-window precomputed tables for resident zkeys), "precomp_c",
  * "h_streams" (1 / 3: a, b, c transform chains on one or three streams), "g2_minb", "warm_max", "reduce_l",
- * "reduce_l_g2", "tree_threads", "timeline" (see b200_last_timeline) */
+ * "reduce_l_g2", "tree_threads", "timeline" (see b200_last_timeline), "fuse_g1" (G1 accumulations sharing a launch: -1 automatic - the three
+ * witness MSMs on a single GPU, all four on a shard; 3: witness MSMs; 4: all four; 0: one launch per MSM) */
 int b200_set_option(b200_ctx *ctx, const char *name, int value);
 
 /* ---- NTT: replaces FFT<Fr>::fft / ifft (fft.hpp:24-25), natural order in and out ------------------ */
@@ -92,6 +93,10 @@ typedef struct b200_zkey_desc {
     /* point-range shard owned by this ctx (multi-GPU): indices [shard_index*len/shard_count, ...) of
      * every table; shard_count = 1 for a single GPU */
     uint32_t shard_index, shard_count;
+    /* optional uneven split (shard_den != 0): this shard owns [len*shard_lo_num/shard_den, len*shard_hi_num/shard_den)
+     * of every table instead - ranks that also run a transform chain of the H pipeline get a smaller share of the
+     * MSMs (rapidsnark_old_b200/dist.py shard_plan).  The shards of one zkey must tile [0, shard_den). */
+    uint32_t shard_lo_num, shard_hi_num, shard_den;
 } b200_zkey_desc;
 
 int b200_zkey_upload(b200_ctx *ctx, const b200_zkey_desc *desc, b200_zkey **out);
@@ -130,17 +135,19 @@ int b200_groth16_prove(b200_ctx *ctx, b200_zkey *zk, const void *wtns, int wtns_
  * b200_prove_begin runs only the chains in poly_mask (bit 0 = a, 1 = b, 2 = c) besides uploading the witness and
  * enqueueing this shard's four witness MSMs, and returns WITHOUT synchronising: d_abc3[0..2] = device pointers of the
  * domain_size x 32-byte a, b, c buffers (coset evaluations, Montgomery), *h_stream = the cudaStream_t they are
- * produced on.  The caller exchanges the buffers so that every rank holds all three (e.g. one NCCL broadcast per
- * polynomial from the rank that owns it, enqueued on / ordered after h_stream), then calls b200_prove_finish:
- * combine -> h, this shard's H MSM, collection of the five partial results (out768 as b200_prove_msms).
+ * produced on.  The caller exchanges the buffers so that every rank holds, of all three, at least the slice
+ * [domain_size * shard_index / shard_count, domain_size * (shard_index + 1) / shard_count) - the only part of h its
+ * H MSM reads (e.g. NCCL sends of those slices from the rank that owns the polynomial, enqueued on / ordered after
+ * h_stream), then calls b200_prove_finish: combine of that slice -> h, this shard's H MSM, collection of the five
+ * partial results (out768 as b200_prove_msms).
  * poly_mask = 7 and no exchange is exactly b200_prove_msms. */
 int b200_prove_begin(b200_ctx *ctx, b200_zkey *zk, const void *wtns, int wtns_on_device, uint32_t poly_mask,
                      void **d_abc3, void **h_stream);
 int b200_prove_finish(b200_ctx *ctx, b200_zkey *zk, void *out768);
 
 /* Exchange step for ONE process driving n GPUs (ctxs[g] / zks[g] = shard g, all after b200_prove_begin with
- * poly_mask = the polynomials i with i % n == g): every transformed polynomial is copied from its owner into the
- * other shards' buffers, device to device (cudaMemcpyPeerAsync over NVLink), ordered on the H streams - the
+ * poly_mask = the polynomials i with i % n == g): of every transformed polynomial each shard receives the slice it
+ * will combine from the owner, device to device (cudaMemcpyPeerAsync over NVLink), ordered on the H streams - the
  * in-process counterpart of the NCCL broadcasts of dist.py.  No host synchronisation. */
 int b200_exchange_polys(b200_ctx *const *ctxs, b200_zkey *const *zks, int n);
 

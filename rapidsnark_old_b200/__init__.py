@@ -58,7 +58,8 @@ class VKey(ctypes.Structure):
 class ZKeyDesc(ctypes.Structure):
     _fields_ = [("n_vars", _u32), ("n_public", _u32), ("domain_size", _u32), ("n_coefs", _u64),
                 ("coefs", _vp), ("points_a", _vp), ("points_b1", _vp), ("points_b2", _vp),
-                ("points_c", _vp), ("points_h", _vp), ("shard_index", _u32), ("shard_count", _u32)]
+                ("points_c", _vp), ("points_h", _vp), ("shard_index", _u32), ("shard_count", _u32),
+                ("shard_lo_num", _u32), ("shard_hi_num", _u32), ("shard_den", _u32)]
 
 
 _lib = None
@@ -319,10 +320,12 @@ class Context:
 
     # ---- zkey residency
     def zkey_upload(self, n_vars, n_public, domain_size, n_coefs, coefs_section, points_a, points_b1, points_b2,
-                    points_c, points_h, shard_index=0, shard_count=1):
+                    points_c, points_h, shard_index=0, shard_count=1, shard_bounds=None):
+        """shard_bounds = (lo_num, hi_num, den): uneven split, this shard owns [len*lo_num/den, len*hi_num/den)."""
+        lo_num, hi_num, den = shard_bounds if shard_bounds else (0, 0, 0)
         keep = [coefs_section, points_a, points_b1, points_b2, points_c, points_h]
         d = ZKeyDesc(n_vars, n_public, domain_size, n_coefs, _ptr(coefs_section), _ptr(points_a), _ptr(points_b1),
-                     _ptr(points_b2), _ptr(points_c), _ptr(points_h), shard_index, shard_count)
+                     _ptr(points_b2), _ptr(points_c), _ptr(points_h), shard_index, shard_count, lo_num, hi_num, den)
         h = _vp()
         self._check(lib().b200_zkey_upload(self.handle, ctypes.byref(d), ctypes.byref(h)))
         return ZKey(self, h, (d, keep))

@@ -86,6 +86,7 @@ void b200_free(b200_ctx *h) {
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t ev : c->evpool) cudaEventDestroy(ev);
     ntt_free_tables(c);
+    msm_g1_fuse_free(c);
     for (int i = 0; i < Ctx::MSM_SLOTS; i++) { if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); if (c->ev_merge[i]) cudaEventDestroy(c->ev_merge[i]); }
     for (int i = 0; i < Ctx::MSM_SLOTS; i++) if (c->side[i]) cudaStreamDestroy(c->side[i]);
     if (c->hstream) cudaStreamDestroy(c->hstream);
@@ -116,6 +117,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "target_tasks_log2")) h->c.opt_target_tasks_log2 = value;
     else if (!strcmp(name, "max_batch_log2")) h->c.opt_max_batch_log2 = value;
     else if (!strcmp(name, "timeline")) h->c.opt_timeline = value;
+    else if (!strcmp(name, "fuse_g1")) h->c.opt_fuse_g1 = value;
     else { h->c.err = std::string("unknown option ") + name; return B200_ERR_ARG; }
     return B200_OK;
 }

@@ -83,6 +83,9 @@ struct Ctx {
     void *pinned = nullptr;            // small pinned host buffer for results
     size_t pinned_cap = 0;
 
+    void *fuse_g1 = nullptr;           // MsmFuse<Fq> of msm_g1.cu: G1 MSMs queued for one fused accumulation launch
+    int opt_fuse_g1 = -1;              // -1 auto, 0 one accumulation launch per MSM, 1 fused (see prove.cu)
+
     struct SlotInfo { int nwin_b = 0, nwin = 0, c = 0, nplanes = 0, L = 0; bool used = false; } slot_info[MSM_SLOTS];
 
     // NTT twiddle tables (built lazily per log-size)
@@ -222,9 +225,14 @@ int msm_g2_run(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t sc
 // asynchronous pair: enqueue all kernels of one MSM (result lands in pinned slot `slot`), collect = wait + host Horner
 // `tail`: no further MSM follows (nothing to overlap the bucket reduction with)
 // `ws`: sort workspace (0/1); `sort_stream`: run the digit sort there (e.g. behind the H pipeline) instead of ctx->stream
+// `defer`: everything up to the accumulation kernel is enqueued, the kernel itself is launched together with those of
+// the other deferred G1 MSMs by msm_g1_flush (one grid for all of them; falls back to an immediate launch when the
+// MSM is not a single-batch table MSM)
 int msm_g1_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
                    const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true, int ws = 0,
-                   cudaStream_t sort_stream = nullptr);
+                   cudaStream_t sort_stream = nullptr, bool defer = false);
+int msm_g1_flush(Ctx *ctx);
+void msm_g1_fuse_free(Ctx *ctx);
 int msm_g2_enqueue(Ctx *ctx, const void *d_bases, const void *d_scalars, uint32_t scalar_size, uint64_t n, int slot,
                    const MsmTableRaw *table = nullptr, bool reuse_sort = false, bool tail = true, int ws = 0,
                    cudaStream_t sort_stream = nullptr);

@@ -92,8 +92,9 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     // kernel's footprint to a few dozen CTAs)
     g.L = g.nbk >= (1u << 18) ? 64 : g.nbk >= (1u << 17) ? 32 : g.nbk >= 16 ? 16 : g.nbk;
     // one shared bucket set (resident tables) below 2^19 buckets = a shard of a multi-GPU zkey: the accumulations
-    // are short, the reduction chains are what the proof waits for (measured at 2 / 4 shards: 16 beats 64 by 7 %)
-    if (shared_buckets && g.nbk < (1u << 19) && g.L > 16) g.L = 16;
+    // are short, the reduction chains are what the proof waits for (round 1, 2 / 4 shards: 16 beats 64 by 7 %;
+    // round 2 with the fused accumulation launch, rank 0 of 8 / of 4: 8 beats 16 by 8 % / 2 %, 4 is worse again)
+    if (shared_buckets && g.nbk < (1u << 19) && g.L > 8) g.L = 8;
     if (tail && g.L > 16) g.L = 16;   // nothing left to overlap with: shortest chains, the whole GPU is free
     g.nseg = g.nbk / g.L;
     g.nplanes = 0;
@@ -458,6 +459,54 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F> *_
     }
 }
 
+// Several MSMs in ONE accumulation launch (blockIdx.y = MSM): the witness MSMs A, B1, C read the same sorted entry
+// list with different tables, H brings its own list.  One grid of all their tasks packs the SMs better than one grid
+// per MSM - a shard of a multi-GPU zkey has only 2^16 tasks per MSM, less than one wave of CTAs - and there is one
+// drain at the end instead of one per MSM.
+template <class F>
+struct MsmAccSet {
+    const Affine<F> *bases;
+    const u32 *entries, *off, *ntasks_ptr, *hot_base;
+    const uint2 *tasks;
+    Xyzz<F> *buckets, *partial;
+    u32 CAP;
+};
+static const int MSM_MAX_FUSE = 4;
+template <class F>
+struct MsmAccSets { MsmAccSet<F> s[MSM_MAX_FUSE]; };
+
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate_sets(const __grid_constant__ MsmAccSets<F> sets) {
+    const MsmAccSet<F> &a = sets.s[blockIdx.y];
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *a.ntasks_ptr) return;
+    const uint2 task = a.tasks[t];
+    const u32 b = task.x, CAP = a.CAP;
+    const u32 o0 = a.off[b], cnt = a.off[b + 1] - o0;
+    const u32 start = o0 + task.y * CAP;
+    const u32 len = (cnt - task.y * CAP < CAP) ? cnt - task.y * CAP : CAP;
+    const u32 *__restrict__ entries = a.entries;
+    const Affine<F> *__restrict__ bases = a.bases;
+
+    RegAcc<F> acc;
+    acc.st_all(Xyzz<F>::zero());
+    u32 e_next = entries[start];
+    Affine<F> p_next = ldg_struct(bases + (e_next & 0x7fffffffu));
+    for (u32 k = 0; k < len; k++) {
+        u32 e = e_next;
+        Affine<F> p = p_next;
+        if (k + 1 < len) {
+            e_next = entries[start + k + 1];
+            p_next = ldg_struct(bases + (e_next & 0x7fffffffu));
+        }
+        if (e >> 31) p.y = fneg(p.y);
+        ec_madd_acc(acc, p);
+    }
+    Xyzz<F> r = acc.get();
+    if (cnt <= CAP) st_struct(a.buckets + b, r);
+    else st_struct(a.partial + a.hot_base[b] + task.y, r);
+}
+
 // CTA-wide tree sum of one XYZZ point per thread; result valid in thread 0.  smem: blockDim.x points
 template <class F>
 DEVFN void cta_tree_sum(Xyzz<F> &acc, Xyzz<F> *sm) {
@@ -650,9 +699,103 @@ int msm_precompute_table(Ctx *ctx, const Affine<F> *d_pts, u32 n, int c, Affine<
     return B200_OK;
 }
 
+// What is left to do for one MSM once its accumulation kernel has been launched (or queued for a fused launch)
+template <class F>
+struct MsmPending {
+    MsmGeom g;
+    int slot = 0, ws = 0;
+    u32 tree_threads = 0, agrid = 0;
+    int add_existing = 0;
+    bool last_batch = true;
+    const Affine<F> *bases = nullptr;
+    u32 *d_hist = nullptr, *d_plan = nullptr, *d_hot_base = nullptr, *d_hot_list = nullptr, *d_warm_list = nullptr, *d_entries = nullptr;
+    uint2 *d_tasks = nullptr;
+    Xyzz<F> *d_buckets = nullptr, *d_partial = nullptr, *d_segs = nullptr, *d_win = nullptr, *h_win = nullptr;
+    cudaStream_t side = nullptr;
+};
+
+// MSMs whose accumulations go into one launch (msm_fuse_flush)
+template <class F>
+struct MsmFuse {
+    int n = 0;
+    MsmPending<F> job[MSM_MAX_FUSE];
+};
+
+// folding of split buckets, then - for the last batch - bucket reduction, window sums and the read-back, on the MSM's
+// side stream: overlaps whatever the main stream does next
+template <class F>
+int msm_post_impl(Ctx *ctx, const MsmPending<F> &p) {
+    typedef Xyzz<F> Pt;
+    const MsmGeom &g = p.g;
+    const int slot = p.slot, ws = p.ws;
+    cudaStream_t st = ctx->stream, side = p.side;
+    B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_ws_acc[ws], st));
+    ctx->ws_acc_pending[ws] = true;
+    cudaStream_t ms = p.last_batch ? side : st;
+    if (p.last_batch) {
+        B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_acc[slot], st));
+        B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(side, ctx->ev_acc[slot], 0));
+    }
+    phase_begin(ctx, PH_MSM_MERGE, ms);
+    // side-stream kernels keep a CTA's register footprint at or below one G1 accumulation CTA (128 x 128
+    // registers), otherwise they only get onto an SM when two of those retire together: 32-thread CTAs for the
+    // per-thread folds, 64-thread trees for G2 (168 registers per thread)
+    B200_LAUNCH_ON(ctx, ms, k_msm_merge_warm<F>, 16 * ctx->sm_count, 32, 0, p.d_hist, g.CAP, p.d_buckets, p.d_partial, p.add_existing, p.d_plan, p.d_hot_base, p.d_warm_list);
+    B200_LAUNCH_ON(ctx, ms, k_msm_merge_hot<F>, 2 * ctx->sm_count, p.tree_threads, p.tree_threads * sizeof(Pt), p.d_hist, g.CAP, p.d_buckets, p.d_partial, p.add_existing, p.d_plan, p.d_hot_base, p.d_hot_list);
+    phase_end(ctx, ms);
+    if (!p.last_batch) return B200_OK;
+    B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_merge[slot], side));
+    ctx->sort_readers[ws] |= 1u << slot;
+
+    // bucket reduction + window sums + D2H on the side stream: overlaps the next MSM's sort / accumulation
+    const u32 total_segs = g.nwin_b * g.nseg, npl1 = g.nplanes + 1;
+    phase_begin(ctx, PH_MSM_REDUCE, side);
+    B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 31) / 32, 32, 0, p.d_buckets, g.nbk, g.L, g.nseg, total_segs, p.d_segs);
+    {
+        // plane sums in two passes: nchunk CTAs per (set, plane), then one CTA per (set, plane) over the chunk sums
+        u32 nchunk = (g.nseg + 1023) / 1024;
+        if (nchunk > 128) nchunk = 128;
+        Pt *d_chunk = p.d_segs + 2 * (size_t)total_segs;
+        B200_LAUNCH_ON(ctx, side, k_msm_plane_sum<F>, dim3(nchunk, npl1, g.nwin_b), p.tree_threads, p.tree_threads * sizeof(Pt), p.d_segs, g.nseg, nchunk, g.nplanes, d_chunk);
+        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, npl1 * g.nwin_b), p.tree_threads, p.tree_threads * sizeof(Pt), d_chunk, nchunk, 1u, p.d_win);
+    }
+    phase_end(ctx, side);
+    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(p.h_win, p.d_win, (size_t)g.nwin_b * npl1 * sizeof(Pt), cudaMemcpyDeviceToHost, side));
+    B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_done[slot], side));
+    ctx->slot_busy[slot] = true;
+    Ctx::SlotInfo &si = ctx->slot_info[slot];
+    si.nwin_b = (int)g.nwin_b; si.nwin = g.nwin; si.c = g.c; si.nplanes = (int)g.nplanes; si.L = (int)g.L; si.used = true;
+    return B200_OK;
+}
+
+// one accumulation launch for all queued MSMs, then each one's post-processing on its own side stream
+template <class F>
+int msm_fuse_flush(Ctx *ctx, MsmFuse<F> *fuse) {
+    if (fuse->n == 0) return B200_OK;
+    MsmAccSets<F> sets;
+    u32 agrid = 0;
+    for (int i = 0; i < fuse->n; i++) {
+        const MsmPending<F> &p = fuse->job[i];
+        MsmAccSet<F> &a = sets.s[i];
+        a.bases = p.bases; a.entries = p.d_entries; a.off = p.d_hist; a.ntasks_ptr = p.d_plan + 2; a.hot_base = p.d_hot_base;
+        a.tasks = p.d_tasks; a.buckets = p.d_buckets; a.partial = p.d_partial; a.CAP = p.g.CAP;
+        if (p.agrid > agrid) agrid = p.agrid;
+    }
+    for (int i = fuse->n; i < MSM_MAX_FUSE; i++) sets.s[i] = sets.s[0];
+    const bool g2 = sizeof(F) != 32;
+    phase_begin(ctx, g2 ? PH_MSM_ACCUM_G2 : PH_MSM_ACCUM);
+    if (g2) B200_LAUNCH(ctx, (k_msm_accumulate_sets<F, 2>), dim3(agrid, fuse->n), 128, 0, sets);
+    else B200_LAUNCH(ctx, (k_msm_accumulate_sets<F, 4>), dim3(agrid, fuse->n), 128, 0, sets);
+    phase_end(ctx);
+    for (int i = 0; i < fuse->n; i++) B200_TRY(msm_post_impl(ctx, fuse->job[i]));
+    fuse->n = 0;
+    return B200_OK;
+}
+
 template <class F>
 int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, uint32_t scalar_size, uint64_t n, int slot,
-                     const MsmTable<F> *table, bool reuse_sort, bool tail, int ws, cudaStream_t sort_stream) {
+                     const MsmTable<F> *table, bool reuse_sort, bool tail, int ws, cudaStream_t sort_stream,
+                     MsmFuse<F> *fuse = nullptr) {
     typedef Xyzz<F> Pt;
     if (slot < 0 || slot >= Ctx::MSM_SLOTS || ws < 0 || ws >= Ctx::SORT_WS) { ctx->err = "msm: bad result slot / workspace"; return B200_ERR_ARG; }
     Ctx::SlotInfo &si = ctx->slot_info[slot];
@@ -765,10 +908,23 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             if (ss != st) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_sort[ws], 0));
         }
 
-        phase_begin(ctx, g2 ? PH_MSM_ACCUM_G2 : PH_MSM_ACCUM);
         const size_t ent = (size_t)nb * g.nwin;
         const size_t tasks_ub = (ent < g.NB ? ent : g.NB) + ent / g.CAP + 1;
         const u32 agrid = (u32)((tasks_ub + 127) / 128);
+        MsmPending<F> pend;
+        pend.g = g; pend.slot = slot; pend.ws = ws; pend.tree_threads = tree_threads; pend.agrid = agrid;
+        pend.add_existing = add_existing; pend.last_batch = base + batch_max >= n; pend.bases = bs;
+        pend.d_hist = d_hist; pend.d_plan = d_plan; pend.d_hot_base = d_hot_base; pend.d_hot_list = d_hot_list;
+        pend.d_warm_list = d_warm_list; pend.d_entries = d_entries; pend.d_tasks = d_tasks;
+        pend.d_buckets = d_buckets; pend.d_partial = d_partial; pend.d_segs = d_segs; pend.d_win = d_win; pend.h_win = h_win;
+        pend.side = side;
+        // a single-batch MSM with the default kernel variant can join a fused launch (msm_fuse_flush)
+        if (fuse && n <= batch_max && ctx->opt_acc_smem <= 0 && fuse->n < MSM_MAX_FUSE && !(g2 && g2_minb == 3)) {
+            fuse->job[fuse->n++] = pend;
+            si.used = false;
+            return B200_OK;
+        }
+        phase_begin(ctx, g2 ? PH_MSM_ACCUM_G2 : PH_MSM_ACCUM);
         {
             // variants: running sum in registers (default) or in shared memory
             void (*kacc)(const Affine<F> *, const u32 *, const u32 *, const uint2 *, const u32 *, u32, const u32 *, Pt *, Pt *, int);
@@ -786,46 +942,8 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             B200_LAUNCH(ctx, kacc, agrid, 128, smem, bs, d_entries, d_hist, d_tasks, d_plan + 2, g.CAP, d_hot_base, d_buckets, d_partial, add_existing);
         }
         phase_end(ctx);
-        B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_ws_acc[ws], st));
-        ctx->ws_acc_pending[ws] = true;
-
-        // folding of split buckets: on the side stream for the last (usually only) batch so that it overlaps the
-        // next MSM's sort and accumulation; earlier batches must finish before the next batch accumulates
-        const bool last_batch = base + batch_max >= n;
-        cudaStream_t ms = last_batch ? side : st;
-        if (last_batch) {
-            B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_acc[slot], st));
-            B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(side, ctx->ev_acc[slot], 0));
-        }
-        phase_begin(ctx, PH_MSM_MERGE, ms);
-        // side-stream kernels keep a CTA's register footprint at or below one G1 accumulation CTA (128 x 128
-        // registers), otherwise they only get onto an SM when two of those retire together: 32-thread CTAs for the
-        // per-thread folds, 64-thread trees for G2 (168 registers per thread)
-        B200_LAUNCH_ON(ctx, ms, k_msm_merge_warm<F>, 16 * ctx->sm_count, 32, 0, d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_warm_list);
-        B200_LAUNCH_ON(ctx, ms, k_msm_merge_hot<F>, 2 * ctx->sm_count, tree_threads, tree_threads * sizeof(Pt), d_hist, g.CAP, d_buckets, d_partial, add_existing, d_plan, d_hot_base, d_hot_list);
-        phase_end(ctx, ms);
-        if (last_batch) {
-            B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_merge[slot], side));
-            ctx->sort_readers[ws] |= 1u << slot;
-        }
+        B200_TRY(msm_post_impl(ctx, pend));
     }
-
-    // bucket reduction + window sums + D2H on the side stream: overlaps the next MSM's sort / accumulation
-    phase_begin(ctx, PH_MSM_REDUCE, side);
-    B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 31) / 32, 32, 0, d_buckets, g.nbk, g.L, g.nseg, total_segs, d_segs);
-    {
-        // plane sums in two passes: nchunk CTAs per (set, plane), then one CTA per (set, plane) over the chunk sums
-        u32 nchunk = (g.nseg + 1023) / 1024;
-        if (nchunk > 128) nchunk = 128;
-        Pt *d_chunk = d_segs + 2 * (size_t)total_segs;
-        B200_LAUNCH_ON(ctx, side, k_msm_plane_sum<F>, dim3(nchunk, npl1, g.nwin_b), tree_threads, tree_threads * sizeof(Pt), d_segs, g.nseg, nchunk, g.nplanes, d_chunk);
-        B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, npl1 * g.nwin_b), tree_threads, tree_threads * sizeof(Pt), d_chunk, nchunk, 1u, d_win);
-    }
-    phase_end(ctx, side);
-    B200_CUDA_CHECK(ctx, cudaMemcpyAsync(h_win, d_win, (size_t)g.nwin_b * npl1 * sizeof(Pt), cudaMemcpyDeviceToHost, side));
-    B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_done[slot], side));
-    ctx->slot_busy[slot] = true;
-    si.nwin_b = (int)g.nwin_b; si.nwin = g.nwin; si.c = g.c; si.nplanes = (int)g.nplanes; si.L = (int)g.L; si.used = true;
     return B200_OK;
 }
 

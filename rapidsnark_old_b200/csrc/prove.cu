@@ -290,9 +290,17 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     zk->ctx = c;
     zk->n_vars = d->n_vars; zk->n_public = d->n_public; zk->domain_size = n; zk->n_coefs = d->n_coefs;
     zk->sharded = cnt > 1;
-    zk->rA = shard_range(d->n_vars, d->shard_index, cnt);
+    if (d->shard_den) {   // explicit (uneven) bounds
+        if (d->shard_lo_num > d->shard_hi_num || d->shard_hi_num > d->shard_den) { delete zk; c->err = "zkey_upload: bad shard bounds"; return B200_ERR_ARG; }
+        zk->rA.lo = (uint64_t)d->n_vars * d->shard_lo_num / d->shard_den;
+        zk->rA.hi = (uint64_t)d->n_vars * d->shard_hi_num / d->shard_den;
+        zk->rH.lo = (uint64_t)n * d->shard_lo_num / d->shard_den;
+        zk->rH.hi = (uint64_t)n * d->shard_hi_num / d->shard_den;
+    } else {
+        zk->rA = shard_range(d->n_vars, d->shard_index, cnt);
+        zk->rH = shard_range(n, d->shard_index, cnt);
+    }
     zk->rC = zk->rA;   // the C table is padded to the witness indexing (see below)
-    zk->rH = shard_range(n, d->shard_index, cnt);
     int rc = B200_OK;
     auto fail = [&](int code) { b200_zkey_free(zk); return code; };
 #define ZK_TRY(x) do { rc = (x); if (rc != B200_OK) return fail(rc); } while (0)
@@ -454,6 +462,7 @@ static void prove_drain(Ctx *c) {
         c->slot_busy[i] = false;
     }
     for (int w = 0; w < Ctx::SORT_WS; w++) { c->sort_readers[w] = 0; c->ws_acc_pending[w] = false; }
+    msm_g1_fuse_free(c);               // MSMs still queued for a fused launch are dropped
     cudaGetLastError();
     c->segs.clear();
     c->ev_used = 0;
@@ -480,14 +489,28 @@ static int prove_stage1_impl(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_
     const uint64_t lenA = zk->rA.hi - zk->rA.lo;
     const bool same_geom = (!zk->tA.tbl == !zk->tB1.tbl) && (!zk->tA.tbl == !zk->tB2.tbl) && (!zk->tA.tbl == !zk->tC.tbl) &&
                            lenA <= (1u << 24);
-    // order: the G2 MSM first (its long bucket reduction then hides behind four G1 accumulations), H last
+    // order: the G2 MSM first (its long bucket reduction then hides behind the G1 accumulations), H last
     B200_TRY(msm_g2_enqueue(c, zk->d_B2, w + zk->rA.lo * 32, 32, lenA, 1, &zk->tB2, false, false));
-    // H pipeline on its own stream, started once the witness digits are sorted (the sort is atomics-bound and would
-    // only be slowed down by the NTT kernels; the G2 accumulation that follows absorbs them)
-    B200_TRY(h_on_device(c, zk, true, lenA ? c->ev_sort[0] : c->ev_h, poly_mask, combine));
-    B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom, false));
-    B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom, false));
-    B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom, false));
+    // H pipeline on its own stream.  One GPU: started once the witness digits are sorted (the sort is atomics-bound
+    // and would only be slowed down by the NTT kernels; the G2 accumulation that follows absorbs them).  A shard of
+    // several: the transform chains, the exchange and the H MSM behind them are the critical path of the proof, the
+    // MSMs are short - the chains start right after the witness upload, beside the sort.
+    B200_TRY(h_on_device(c, zk, true, (lenA && !zk->sharded) ? c->ev_sort[0] : c->ev_h, poly_mask, combine));
+    // The three witness G1 MSMs read one sorted entry list: with resident tables their accumulations go into ONE
+    // launch (msm.cuh k_msm_accumulate_sets).  A single GPU that also combines here (no exchange in between) adds the
+    // H MSM to the same launch in prove_enqueue_h: the H pipeline finishes under the G2 accumulation, so nothing waits.
+    // Measured on B200 (profiles/r02_fuse_ab.md): on one GPU the three witness MSMs in one launch and H in a second one
+    // is best (the witness MSMs' bucket reductions hide under the H accumulation; all four at once leaves four
+    // reductions for the tail); on a shard the reductions are latency-bound and equally long alone or together, so all
+    // four accumulations share one launch.  Option "fuse_g1": -1 auto, 0 one launch per MSM (round 1), 3 witness MSMs
+    // only, 4 all four.
+    const bool fuse = c->opt_fuse_g1 != 0 && same_geom && zk->tA.tbl;
+    const bool with_h = fuse && (c->opt_fuse_g1 == 4 || (c->opt_fuse_g1 != 3 && zk->sharded));
+    // with H in the same launch nothing follows the four accumulations: every bucket reduction is a "tail" one
+    B200_TRY(msm_g1_enqueue(c, zk->d_A, w + zk->rA.lo * 32, 32, lenA, 2, &zk->tA, same_geom, with_h, 0, nullptr, fuse));
+    B200_TRY(msm_g1_enqueue(c, zk->d_B1, w + zk->rA.lo * 32, 32, lenA, 3, &zk->tB1, same_geom, with_h, 0, nullptr, fuse));
+    B200_TRY(msm_g1_enqueue(c, zk->d_C, w + zk->rA.lo * 32, 32, lenA, 4, &zk->tC, same_geom, with_h, 0, nullptr, fuse));
+    if (fuse && !with_h) B200_TRY(msm_g1_flush(c));   // else: launched together with H by prove_enqueue_h
     zk->stage1_done = true;
     zk->stage1_combined = combine;
     return B200_OK;
@@ -509,15 +532,19 @@ static int prove_enqueue_h(Ctx *c, b200_zkey *zk) {
         cudaStream_t main_stream = c->stream;
         c->stream = c->hstream;
         phase_begin(c, PH_NTT);
-        int rc = h_combine(c, zk->d_a, zk->d_b, zk->d_c, zk->domain_size);
+        // only this shard's slice of h is ever read (its range of the H table): the exchange before this call need
+        // not deliver more than that slice of a, b and c
+        const uint64_t lo = zk->rH.lo, len = zk->rH.hi - zk->rH.lo;
+        int rc = len ? h_combine(c, zk->d_a + lo, zk->d_b + lo, zk->d_c + lo, len) : B200_OK;
         phase_end(c);
         c->stream = main_stream;
         B200_TRY(rc);
     }
     // the digit sort of h runs on the H-pipeline stream right behind the NTTs (own sort workspace), i.e. under the
     // witness accumulations; only the H accumulation itself waits for it on the main stream
-    return msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true,
-                          1, c->hstream);
+    B200_TRY(msm_g1_enqueue(c, zk->d_H, (const uint8_t *)zk->d_a + zk->rH.lo * 32, 32, zk->rH.hi - zk->rH.lo, 0, &zk->tH, false, true,
+                            1, c->hstream, c->opt_fuse_g1 != 0));
+    return msm_g1_flush(c);     // H alone, or H together with the witness MSMs still queued by stage 1
 }
 
 static int prove_sync_all(Ctx *c) {
@@ -614,7 +641,6 @@ int b200_exchange_polys(b200_ctx *const *hs, b200_zkey *const *zks, int n) {
             if (hs[g]) hs[g]->c.err = "exchange_polys: every shard needs a pending b200_prove_begin of the same circuit";
             return B200_ERR_ARG;
         }
-    const size_t bytes = (size_t)zks[0]->domain_size * sizeof(Fr);
     for (int i = 0; i < 3; i++) {
         const int o = i % n;
         Ctx *co = &hs[o]->c;
@@ -623,6 +649,9 @@ int b200_exchange_polys(b200_ctx *const *hs, b200_zkey *const *zks, int n) {
             if (r == o) continue;
             Ctx *cr = &hs[r]->c;
             Fr *dst = i == 0 ? zks[r]->d_a : i == 1 ? zks[r]->d_b : zks[r]->d_c;
+            // shard r combines (and reads) only its own range of h: that slice of the polynomial is all it needs
+            const size_t lo = (size_t)zks[r]->rH.lo, bytes = (size_t)(zks[r]->rH.hi - zks[r]->rH.lo) * sizeof(Fr);
+            if (bytes == 0) continue;
             cudaSetDevice(cr->device);
             if (cr->device != co->device && !(cr->peer_enabled & (1ull << co->device)) && co->device < 64) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(co->device, 0);   // direct NVLink path when available
@@ -631,7 +660,7 @@ int b200_exchange_polys(b200_ctx *const *hs, b200_zkey *const *zks, int n) {
             }
             // co->ev_h: recorded on the owner's H stream behind its transform chains (h_on_device)
             B200_CUDA_CHECK(cr, cudaStreamWaitEvent(cr->hstream, co->ev_h, 0));
-            B200_CUDA_CHECK(cr, cudaMemcpyPeerAsync(dst, cr->device, src, co->device, bytes, cr->hstream));
+            B200_CUDA_CHECK(cr, cudaMemcpyPeerAsync(dst + lo, cr->device, src + lo, co->device, bytes, cr->hstream));
         }
     }
     // Write-after-read: the combine of b200_prove_finish overwrites d_a IN PLACE on the owner's H stream, while the

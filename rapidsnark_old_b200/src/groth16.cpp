@@ -84,6 +84,7 @@ Prover<Engine>::Prover(uint32_t _nVars, uint32_t _nPublic, uint32_t _domainSize,
         d.coefs = coefs; d.points_a = pointsA; d.points_b1 = pointsB1; d.points_b2 = pointsB2;
         d.points_c = pointsC; d.points_h = pointsH;
         d.shard_index = (uint32_t)g; d.shard_count = (uint32_t)nGpus;
+        d.shard_lo_num = d.shard_hi_num = d.shard_den = 0;
         int rc = b200_zkey_upload(gp.ctx, &d, &gp.zk);
         if (rc != B200_OK) {
             std::string msg = std::string("b200_zkey_upload: ") + b200_last_error(gp.ctx);

@@ -295,13 +295,18 @@ class FastSynth:
     build_points = Synth.build_points
 
     # ---- one shard's slices only (multi-GPU runs of big circuits: 2^26 tables are 24 GB, times eight ranks)
-    def build_shard_points(self, g1_mul_many, g2_mul_many, index, count):
+    def build_shard_points(self, g1_mul_many, g2_mul_many, index, count, bounds=None):
         """Point tables restricted to what b200_zkey_upload reads for shard `index` of `count` (same partition rule:
-        [len * index / count, len * (index + 1) / count) of the witness-indexed tables and of H).  Fills
+        [len * index / count, len * (index + 1) / count) of the witness-indexed tables and of H - or, with
+        bounds = (lo_num, hi_num, den), [len * lo_num / den, len * hi_num / den)).  Fills
         self.shard_points = {name: (bytes, first_point_index)} and self.vk; see shard_table_address()."""
         V, P, n = self.n_vars, self.n_public, self.n
-        lo, hi = V * index // count, V * (index + 1) // count
-        hlo, hhi = n * index // count, n * (index + 1) // count
+        if bounds:
+            lo, hi = V * bounds[0] // bounds[2], V * bounds[1] // bounds[2]
+            hlo, hhi = n * bounds[0] // bounds[2], n * bounds[1] // bounds[2]
+        else:
+            lo, hi = V * index // count, V * (index + 1) // count
+            hlo, hhi = n * index // count, n * (index + 1) // count
         skip = P + 1
         clo, chi = max(lo, skip) - skip, max(hi, skip) - skip          # C table: signals skip .. V-1
         cut = lambda b, a, z: b[32 * a:32 * z]

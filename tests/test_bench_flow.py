@@ -52,7 +52,8 @@ class _FakeContext:
         self.fixed_base_g1 = lambda base, ks, n: g1m(unpack(ks))
         self.fixed_base_g2 = lambda base, ks, n: g2m(unpack(ks))
 
-    def zkey_upload(self, *args):
+    def zkey_upload(self, *args, shard_bounds=None):
+        assert shard_bounds is None            # one GPU: no explicit bounds
         return _FakeZKey(self, args)
 
     def set_option(self, k, v):
@@ -99,7 +100,7 @@ def test_own_arm_flow_with_stand_ins(monkeypatch):
     monkeypatch.setenv("RANK", "0")
     monkeypatch.setenv("LOCAL_RANK", "0")
     args = types.SimpleNamespace(gpus=1, steps=2, warmup=3, impl="own", log_n=6, no_cpu_baseline=False, emulate_shards=0,
-                                 opt=[], replicate_h=False, shard_inputs=False)
+                                 opt=[], replicate_h=False, shard_inputs=False, emulate_poly_mask=-1, even_shards=False, emulate_rank=0)
     out = io.StringIO()
     with redirect_stdout(out):
         assert bench.run_own(args) == 0

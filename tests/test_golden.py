@@ -126,17 +126,20 @@ def _exchange_worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     owners = bdist.poly_owners(world)
     # every rank fills only the polynomials it owns (value = 10 * poly + owner), the rest is garbage
-    polys = [torch.full((64,), 10 * i + o if o == rank else 255, dtype=torch.uint8) for i, o in enumerate(owners)]
+    n = 24                                   # "domain" of 24 elements of 32 bytes: 24 splits evenly and unevenly
+    polys = [torch.full((n * 32,), 10 * i + o if o == rank else 255, dtype=torch.uint8) for i, o in enumerate(owners)]
     bdist.exchange_polys(polys)
-    q.put((rank, bdist.poly_mask(rank, world), [int(p[0]) for p in polys], [bool((p == p[0]).all()) for p in polys]))
+    lo, hi = bdist.plan_range(n, rank, world)
+    mine = [p[lo * 32:hi * 32] for p in polys]            # the slice this rank combines
+    q.put((rank, bdist.poly_mask(rank, world), [int(p[0]) for p in mine], [bool((p == p[0]).all()) for p in mine]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 5])
 def test_h_polynomial_exchange_over_gloo(world):
-    """N > 1 host logic of the H-pipeline split: ownership masks cover a, b, c exactly once and one broadcast per
-    polynomial leaves every rank with all three (dist.exchange_polys; NCCL on the GPU box, gloo here)."""
+    """N > 1 host logic of the H-pipeline split: ownership masks cover a, b, c exactly once and the point-to-point
+    exchange leaves every rank with ITS slice of all three (dist.exchange_polys; NCCL on the GPU box, gloo here)."""
     import torch.multiprocessing as mp
     from rapidsnark_old_b200 import dist as bdist
     ctx = mp.get_context("spawn")

@@ -281,6 +281,29 @@ def test_sharded_prove_folds_to_unsharded(ctx, orc, shards):
     assert orc.msms_to_affine(folded) == synth_util.expected_affine(orc, s)
 
 
+@pytest.mark.parametrize("shards,chain_cost", [(2, 0.033), (4, 0.15), (8, 0.033)])
+def test_uneven_shard_plan_folds_to_unsharded(ctx, orc, shards, chain_cost):
+    """explicit shard bounds (b200_zkey_desc.shard_lo_num / hi_num / den, dist.shard_plan: ranks that run a transform
+    chain own a smaller point range): the partials still fold to the full result."""
+    from rapidsnark_old_b200 import dist as bdist
+    s = synth_util.make(10)
+    wt = s.wtns_bytes()
+    plan = bdist.shard_plan(shards, chain_cost)
+    assert plan[0][0] == 0 and plan[-1][1] == bdist.PLAN_DEN and all(plan[i][1] == plan[i + 1][0] for i in range(shards - 1))
+    assert plan[0][1] - plan[0][0] < plan[-1][1] - plan[-1][0]          # rank 0 runs a chain: smaller share
+    parts = []
+    p = s.points
+    for i in range(shards):
+        zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"], p["H"],
+                             i, shards, shard_bounds=plan[i] + (bdist.PLAN_DEN,))
+        parts.append(zk.prove_msms(wt))
+        zk.free()
+    assert orc.msms_to_affine(b200.fold_partials(parts)) == synth_util.expected_affine(orc, s)
+    with pytest.raises(b200.B200Error):
+        ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"], p["H"],
+                        0, 2, shard_bounds=(5, 3, 8))
+
+
 def test_two_stage_prove_equals_one_call(ctx, orc):
     """b200_prove_begin(poly_mask = 7) + b200_prove_finish is b200_prove_msms."""
     s = synth_util.make(10)
