@@ -277,7 +277,9 @@ def run_own(args):
         bounds = eplan[er] + (bdist.PLAN_DEN,)
         if args.emulate_poly_mask == -2:
             args.emulate_poly_mask = bdist.poly_mask(er, emu)
-    zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section(), p["A"], p["B1"], p["B2"], p["C"],
+    # a rank that runs no transform chain never reads the coefficients: it uploads the zkey without section 4
+    need_coefs = world == 1 or emu or args.replicate_h or bdist.poly_mask(rank, world) != 0
+    zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section() if need_coefs else None, p["A"], p["B1"], p["B2"], p["C"],
                          p["H"], args.emulate_rank if emu else rank, emu if emu else world, shard_bounds=bounds if (world > 1 or emu) else None)
     wt_bytes = s.wtns_bytes()
     # witness: pinned host copy (e2e) and device copy (value)

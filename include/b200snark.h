@@ -84,7 +84,9 @@ int b200_ntt_fr_dev(b200_ctx *ctx, void *d_a, uint64_t n, int inverse);
 typedef struct b200_zkey_desc {
     uint32_t n_vars, n_public, domain_size;
     uint64_t n_coefs;
-    const void *coefs;    /* zkey section 4 payload: u32 count, then n_coefs 44-byte records (groth16.hpp:27-35) */
+    const void *coefs;    /* zkey section 4 payload: u32 count, then n_coefs 44-byte records (groth16.hpp:27-35).
+                           * May be NULL when shard_count > 1 for a shard that never builds a, b, c itself
+                           * (b200_prove_begin with poly_mask = 0: it receives its slices from the owners) */
     const void *points_a; /* n_vars G1 */
     const void *points_b1;/* n_vars G1 */
     const void *points_b2;/* n_vars G2 */

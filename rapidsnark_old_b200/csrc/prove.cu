@@ -6,9 +6,13 @@
 // so that the a/b build (groth16.cpp:62-85, 1024 striped locks on the CPU) is a lock-free row gather.
 // b200_prove_msms is groth16.cpp:52-207: a,b,c -> 3 x (ifft, coset twist, fft) -> h -> five MSMs.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <vector>
 #include "ctx.cuh"
 #include "memops.cuh"
+#include "scan.cuh"
 
 namespace b200 {
 int ntt_natural(Ctx *ctx, Fr *d_a, uint64_t n, bool inverse);
@@ -31,6 +35,7 @@ struct b200_zkey {
     Range rA, rC, rH;       // this shard's index ranges (A, B1, B2 share rA)
     bool stage1_done = false, stage1_combined = false;   // b200_prove_begin / b200_prove_finish pairing
     bool sharded = false;   // shard_count > 1: small MSMs, the (replicated) H pipeline is the critical path
+    bool has_coefs = true;  // false: uploaded without the coefficient section (a shard that only receives a, b, c)
     u32 *d_row_a = nullptr, *d_row_b = nullptr, *d_sig = nullptr;
     Fr *d_coef = nullptr;
     G1Affine *d_A = nullptr, *d_B1 = nullptr, *d_C = nullptr, *d_H = nullptr;   // plain shard slices, or
@@ -68,14 +73,120 @@ static int table_window_bits(uint64_t len) {
     return best;
 }
 
+// ---- ingestion (reference: src/binfile_utils.cpp:14-64 reads the file into a malloc'd copy) ------------
+// The zkey sections arrive as pointers into the caller's mmap of the file: pageable memory.  Two ways to the device:
+// plain cudaMemcpyAsync (the driver stages through its own pinned buffers), or - B200_STAGING=1 - a few host threads
+// that copy 8 MB chunks into their own pinned buffers and issue the H2D copies from those.  Measured on the B200 box
+// at 2^20 (0.54 GB zkey, page cache warm, profiles/r02_cli_bench.json): plain 58 ms for the whole upload including
+// the device-side CSR build, staged 93 ms - allocating the pinned buffers costs more than the overlap saves - so the
+// plain path is the default.
+static const size_t STAGE_CHUNK = 8u << 20;
+static const int STAGE_THREADS = 4;
+
+struct Stager {
+    void *buf[STAGE_THREADS] = {nullptr};
+    cudaStream_t st[STAGE_THREADS] = {nullptr};
+    cudaEvent_t ev[STAGE_THREADS] = {nullptr};
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        for (int i = 0; i < STAGE_THREADS; i++) {
+            if (cudaHostAlloc(&buf[i], STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) return false;
+            if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        ok = true;
+        return true;
+    }
+    void release() {
+        for (int i = 0; i < STAGE_THREADS; i++) {
+            if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            if (buf[i]) cudaFreeHost(buf[i]);
+            buf[i] = nullptr; st[i] = nullptr; ev[i] = nullptr;
+        }
+        ok = false;
+    }
+};
+
+struct CopyJob { void *dst; const void *src; size_t bytes; };
+
+// all jobs, chunk by chunk, over the staging threads; returns when every byte is on the device
+static int staged_upload(Ctx *c, const std::vector<CopyJob> &jobs) {
+    size_t total = 0;
+    for (auto &j : jobs) total += j.bytes;
+    static const bool on = getenv("B200_STAGING") != nullptr && atoi(getenv("B200_STAGING")) != 0;
+    Stager sg;
+    if (!on || total < (64u << 20) || !sg.init()) {
+        sg.release();
+        cudaGetLastError();
+        for (auto &j : jobs)
+            if (j.bytes) B200_CUDA_CHECK(c, cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, c->stream));
+        B200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        return B200_OK;
+    }
+    struct Chunk { uint8_t *dst; const uint8_t *src; size_t bytes; };
+    std::vector<Chunk> chunks;
+    for (auto &j : jobs)
+        for (size_t o = 0; o < j.bytes; o += STAGE_CHUNK)
+            chunks.push_back({(uint8_t *)j.dst + o, (const uint8_t *)j.src + o, std::min(STAGE_CHUNK, j.bytes - o)});
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    const int dev = c->device;
+    auto work = [&](int t) {
+        cudaSetDevice(dev);
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= chunks.size() || failed.load()) break;
+            if (cudaEventSynchronize(sg.ev[t]) != cudaSuccess) { failed = 1; break; }   // this buffer's last copy is out
+            memcpy(sg.buf[t], chunks[i].src, chunks[i].bytes);
+            if (cudaMemcpyAsync(chunks[i].dst, sg.buf[t], chunks[i].bytes, cudaMemcpyHostToDevice, sg.st[t]) != cudaSuccess ||
+                cudaEventRecord(sg.ev[t], sg.st[t]) != cudaSuccess) { failed = 1; break; }
+        }
+        cudaStreamSynchronize(sg.st[t]);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < STAGE_THREADS; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    sg.release();
+    if (failed.load()) { c->err = "zkey_upload: staged host-to-device copy failed"; cudaGetLastError(); return B200_ERR_CUDA; }
+    return B200_OK;
+}
+
 template <class T>
-static int upload_slice(Ctx *c, T **dst, const void *src, Range r) {
+static int alloc_slice(Ctx *c, T **dst, const void *src, Range r, std::vector<CopyJob> &jobs) {
     size_t cnt = (size_t)(r.hi - r.lo);
     B200_CUDA_CHECK(c, cudaMalloc((void **)dst, std::max<size_t>(cnt, 1) * sizeof(T)));
-    if (cnt)
-        B200_CUDA_CHECK(c, cudaMemcpyAsync(*dst, (const uint8_t *)src + (size_t)r.lo * sizeof(T), cnt * sizeof(T),
-                                            cudaMemcpyHostToDevice, c->stream));
+    if (cnt) jobs.push_back({*dst, (const uint8_t *)src + (size_t)r.lo * sizeof(T), cnt * sizeof(T)});
     return B200_OK;
+}
+
+// ---- CSR build of the coefficient records on the device (reference: groth16.cpp:62-85 walks the packed 44-byte
+// records {u32 m, u32 c, u32 s, Fr coef} with 1024 striped locks).  Rows of A then rows of B share one offset array:
+// off[m * n + row]; the order of the entries inside a row is arbitrary - their sum is exact field arithmetic.
+static __global__ void __launch_bounds__(256) k_coef_count(const u32 *__restrict__ rec, u64 n_coefs, u32 n, u32 n_vars,
+                                                            u32 *__restrict__ cnt, u32 *__restrict__ bad) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_coefs) return;
+    const u32 *r = rec + i * 11;
+    u32 m = r[0], row = r[1], sg = r[2];
+    if (m > 1 || row >= n || sg >= n_vars) { atomicOr(bad, 1u); return; }
+    atomicAdd(&cnt[(size_t)m * n + row], 1u);
+}
+
+static __global__ void __launch_bounds__(256) k_coef_place(const u32 *__restrict__ rec, u64 n_coefs, u32 n,
+                                                            u32 *__restrict__ cursor, u32 *__restrict__ sig, Fr *__restrict__ coef) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_coefs) return;
+    const u32 *r = rec + i * 11;
+    u32 m = r[0], row = r[1];
+    u32 k = atomicAdd(&cursor[(size_t)m * n + row], 1u);
+    sig[k] = r[2];
+    Fr v;
+#pragma unroll
+    for (int j = 0; j < 8; j++) v.v[j] = r[3 + j];
+    st_struct(coef + k, v);
 }
 
 // ---- fixed-base tables (synthetic zkey generation; not on the prove path) ---------------------------
@@ -187,7 +298,7 @@ int b200_ntt_fr(b200_ctx *h, void *a_host, uint64_t n, int inverse) {
 
 // ---------------------------------------------------------------------------------------------- zkey
 static void zkey_free_tables(b200_zkey *zk) {
-    void *all[] = {zk->d_row_a, zk->d_row_b, zk->d_sig, zk->d_coef, zk->d_A, zk->d_B1, zk->d_C, zk->d_H, zk->d_B2};
+    void *all[] = {zk->d_row_a /* d_row_b is part of it */, zk->d_sig, zk->d_coef, zk->d_A, zk->d_B1, zk->d_C, zk->d_H, zk->d_B2};
     for (void *p : all) if (p) cudaFree(p);
     delete zk;
 }
@@ -241,12 +352,16 @@ int b200_zkey_share(b200_ctx *h, b200_zkey *src, b200_zkey **out) {
     return B200_OK;
 }
 
+static bool cnt_is_one(const b200_zkey_desc *d) { return d->shard_count <= 1; }
+
 int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     if (!h || !d || !out) return B200_ERR_ARG;
     Ctx *c = &h->c;
     *out = nullptr;
     cudaSetDevice(c->device);
-    if (!d->coefs || !d->points_a || !d->points_b1 || !d->points_b2 || !d->points_c || !d->points_h) {
+    // coefs may be NULL for a shard that never builds a, b, c itself (it receives them: b200_prove_begin with
+    // poly_mask = 0) - five of eight ranks then skip 44 bytes per coefficient of host reads, upload and CSR build
+    if ((!d->coefs && cnt_is_one(d)) || !d->points_a || !d->points_b1 || !d->points_b2 || !d->points_c || !d->points_h) {
         c->err = "zkey_upload: null section pointer"; return B200_ERR_ARG;
     }
     const u32 n = d->domain_size;
@@ -255,36 +370,6 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     if (d->n_vars == 0 || d->n_public + 1 > d->n_vars) { c->err = "zkey_upload: bad n_vars / n_public"; return B200_ERR_ARG; }
     const u32 cnt = d->shard_count ? d->shard_count : 1;
     if (d->shard_index >= cnt) { c->err = "zkey_upload: shard_index >= shard_count"; return B200_ERR_ARG; }
-
-    // CSR repack of section 4 (records start after the u32 count: groth16.cpp:38)
-    const uint8_t *rec = (const uint8_t *)d->coefs + 4;
-    std::vector<u32> row_a(n + 1, 0), row_b(n + 1, 0);
-    for (u64 i = 0; i < d->n_coefs; i++) {
-        u32 m, r, s;
-        memcpy(&m, rec + i * 44, 4);
-        memcpy(&r, rec + i * 44 + 4, 4);
-        memcpy(&s, rec + i * 44 + 8, 4);
-        if (m > 1 || r >= n || s >= d->n_vars) { c->err = "zkey_upload: coefficient record out of range"; return B200_ERR_ARG; }
-        (m == 0 ? row_a : row_b)[r + 1]++;
-    }
-    for (u32 r = 0; r < n; r++) row_a[r + 1] += row_a[r];
-    const u32 nnz_a = row_a[n];
-    row_b[0] = nnz_a;
-    for (u32 r = 0; r < n; r++) row_b[r + 1] += row_b[r];
-    std::vector<u32> sig(d->n_coefs ? d->n_coefs : 1);
-    std::vector<Fr> coef(d->n_coefs ? d->n_coefs : 1);
-    {
-        std::vector<u32> cur_a(row_a.begin(), row_a.end() - 1), cur_b(row_b.begin(), row_b.end() - 1);
-        for (u64 i = 0; i < d->n_coefs; i++) {
-            u32 m, r, s;
-            memcpy(&m, rec + i * 44, 4);
-            memcpy(&r, rec + i * 44 + 4, 4);
-            memcpy(&s, rec + i * 44 + 8, 4);
-            u32 k = (m == 0 ? cur_a : cur_b)[r]++;
-            sig[k] = s;
-            memcpy(&coef[k], rec + i * 44 + 12, 32);
-        }
-    }
 
     b200_zkey *zk = new b200_zkey();
     zk->ctx = c;
@@ -305,28 +390,74 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     auto fail = [&](int code) { b200_zkey_free(zk); return code; };
 #define ZK_TRY(x) do { rc = (x); if (rc != B200_OK) return fail(rc); } while (0)
 #define ZK_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { c->err = std::string("zkey_upload: ") + cudaGetErrorString(e_); return fail(B200_ERR_CUDA); } } while (0)
-    ZK_CUDA(cudaMalloc(&zk->d_row_a, (size_t)(n + 1) * 4));
-    ZK_CUDA(cudaMalloc(&zk->d_row_b, (size_t)(n + 1) * 4));
-    ZK_CUDA(cudaMalloc(&zk->d_sig, sig.size() * 4));
-    ZK_CUDA(cudaMalloc(&zk->d_coef, coef.size() * sizeof(Fr)));
-    ZK_CUDA(cudaMemcpyAsync(zk->d_row_a, row_a.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    ZK_CUDA(cudaMemcpyAsync(zk->d_row_b, row_b.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    ZK_CUDA(cudaMemcpyAsync(zk->d_sig, sig.data(), sig.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    ZK_CUDA(cudaMemcpyAsync(zk->d_coef, coef.data(), coef.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-    ZK_TRY(upload_slice(c, &zk->d_A, d->points_a, zk->rA));
-    ZK_TRY(upload_slice(c, &zk->d_B1, d->points_b1, zk->rA));
-    ZK_TRY(upload_slice(c, &zk->d_B2, d->points_b2, zk->rA));
+    // every section goes to the device through the staged uploader; the coefficient records as they are in the file
+    // (the CSR arrays are built from them on the device, below)
+    std::vector<CopyJob> jobs;
+    u32 *d_rec = nullptr;                       // raw 44-byte records (section 4 after the u32 count: groth16.cpp:38)
+    const bool have_coefs = d->coefs != nullptr && d->n_coefs > 0;
+    if (have_coefs) {
+        ZK_CUDA(cudaMalloc(&d_rec, (size_t)d->n_coefs * 44));
+        jobs.push_back({d_rec, (const uint8_t *)d->coefs + 4, (size_t)d->n_coefs * 44});
+    }
+    ZK_TRY(alloc_slice(c, &zk->d_A, d->points_a, zk->rA, jobs));
+    ZK_TRY(alloc_slice(c, &zk->d_B1, d->points_b1, zk->rA, jobs));
+    ZK_TRY(alloc_slice(c, &zk->d_B2, d->points_b2, zk->rA, jobs));
     {   // C is stored aligned with the witness: (n_public + 1) leading points at infinity, so the A, B1, B2 and C
         // MSMs all read the same scalars and can share one digit sort (zero bases are skipped by the mixed add)
         const uint64_t lo = zk->rA.lo, hi = zk->rA.hi, skip = (uint64_t)d->n_public + 1;
         ZK_CUDA(cudaMalloc((void **)&zk->d_C, std::max<size_t>(hi - lo, 1) * sizeof(G1Affine)));
         ZK_CUDA(cudaMemsetAsync(zk->d_C, 0, std::max<size_t>(hi - lo, 1) * sizeof(G1Affine), c->stream));
+        ZK_CUDA(cudaStreamSynchronize(c->stream));       // the staged copies below run on other streams
         const uint64_t from = std::max(lo, skip);
         if (hi > from)
-            ZK_CUDA(cudaMemcpyAsync(zk->d_C + (from - lo), (const uint8_t *)d->points_c + (from - skip) * sizeof(G1Affine),
-                                    (hi - from) * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
+            jobs.push_back({zk->d_C + (from - lo), (const uint8_t *)d->points_c + (from - skip) * sizeof(G1Affine),
+                            (size_t)(hi - from) * sizeof(G1Affine)});
     }
-    ZK_TRY(upload_slice(c, &zk->d_H, d->points_h, zk->rH));
+    ZK_TRY(alloc_slice(c, &zk->d_H, d->points_h, zk->rH, jobs));
+    if (int up = staged_upload(c, jobs)) { if (d_rec) cudaFree(d_rec); return fail(up); }
+    // CSR arrays: off[0 .. n] = row starts of A, off[n .. 2n] = row starts of B (one exclusive scan over the 2n counts)
+    {
+        const size_t rows = 2 * (size_t)n + 1, rows_pad = (rows + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
+        const u32 ntiles = (u32)(rows_pad / SCAN_TILE);
+        const size_t nc = have_coefs ? (size_t)d->n_coefs : 1;
+        u32 *d_cur = nullptr, *d_tot = nullptr, *d_bad = nullptr;
+        ZK_CUDA(cudaMalloc(&zk->d_row_a, rows_pad * 4));
+        zk->d_row_b = zk->d_row_a + n;              // same allocation
+        ZK_CUDA(cudaMalloc(&zk->d_sig, nc * 4));
+        ZK_CUDA(cudaMalloc(&zk->d_coef, nc * sizeof(Fr)));
+        ZK_CUDA(cudaMemsetAsync(zk->d_row_a, 0, rows_pad * 4, c->stream));
+        if (have_coefs) {
+            cudaError_t e = cudaMalloc(&d_cur, rows_pad * 4);
+            if (e == cudaSuccess) e = cudaMalloc(&d_tot, (size_t)ntiles * 4 + 16);
+            if (e == cudaSuccess) e = cudaMalloc(&d_bad, 4);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, c->stream);
+            u32 bad = 0;
+            if (e == cudaSuccess) {
+                const u32 grid = (u32)((d->n_coefs + 255) / 256);
+                k_coef_count<<<grid, 256, 0, c->stream>>>(d_rec, d->n_coefs, n, d->n_vars, zk->d_row_a, d_bad);
+                k_scan_tile<<<ntiles, 1024, 0, c->stream>>>(zk->d_row_a, d_tot);
+                k_scan_totals<<<1, 1024, 0, c->stream>>>(d_tot, ntiles);
+                k_scan_add<<<ntiles, 1024, 0, c->stream>>>(zk->d_row_a, d_tot, d_cur);
+                c->launches += 4;
+                e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+                if (e == cudaSuccess && !bad) {
+                    k_coef_place<<<grid, 256, 0, c->stream>>>(d_rec, d->n_coefs, n, d_cur, zk->d_sig, zk->d_coef);
+                    c->launches++;
+                    e = cudaStreamSynchronize(c->stream);
+                }
+                if (e == cudaSuccess) e = cudaGetLastError();
+            }
+            if (d_cur) cudaFree(d_cur);
+            if (d_tot) cudaFree(d_tot);
+            if (d_bad) cudaFree(d_bad);
+            cudaFree(d_rec);
+            d_rec = nullptr;
+            if (e != cudaSuccess) { c->err = std::string("zkey_upload: ") + cudaGetErrorString(e); return fail(B200_ERR_CUDA); }
+            if (bad) { c->err = "zkey_upload: coefficient record out of range"; return fail(B200_ERR_ARG); }
+        }
+        zk->has_coefs = have_coefs || d->n_coefs == 0;
+    }
     // resident per-window tables (msm.cuh): all windows of an MSM share one bucket set
     {
         // window width of the tables: about log2(points) (measured on B200: 2^20 points -> c = 20 beats 16..19),
@@ -380,7 +511,7 @@ int b200_zkey_upload(b200_ctx *h, const b200_zkey_desc *d, b200_zkey **out) {
     ZK_CUDA(cudaMalloc(&zk->d_a, (size_t)n * sizeof(Fr)));
     ZK_CUDA(cudaMalloc(&zk->d_b, (size_t)n * sizeof(Fr)));
     ZK_CUDA(cudaMalloc(&zk->d_c, (size_t)n * sizeof(Fr)));
-    ZK_CUDA(cudaStreamSynchronize(c->stream));   // host staging vectors die at return
+    ZK_CUDA(cudaStreamSynchronize(c->stream));
 #undef ZK_TRY
 #undef ZK_CUDA
     *out = zk;
@@ -434,6 +565,7 @@ int b200_h_scalars(b200_ctx *h, b200_zkey *zk, const void *wtns_host, void *h_ou
     if (!h || !zk || !wtns_host || !h_out_host) return B200_ERR_ARG;
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
+    if (!zk->has_coefs) { c->err = "h_scalars: this zkey was uploaded without the coefficient section"; return B200_ERR_ARG; }
     phase_reset(c);
     B200_TRY(wtns_upload(c, zk, wtns_host, false));
     B200_TRY(h_on_device(c, zk));
@@ -479,6 +611,7 @@ static int prove_stage1(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_de
 
 static int prove_stage1_impl(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_on_device, unsigned poly_mask, bool combine) {
     cudaSetDevice(c->device);
+    if (poly_mask && !zk->has_coefs) { c->err = "prove: this zkey was uploaded without the coefficient section (it cannot build a, b, c)"; return B200_ERR_ARG; }
     phase_reset(c);
     B200_TRY(wtns_upload(c, zk, wtns, wtns_on_device, poly_mask == 0 && !combine));
     B200_CUDA_CHECK(c, cudaEventRecord(c->ev_h, c->stream));   // "witness uploaded"

@@ -1,5 +1,7 @@
 #include "groth16.hpp"
+#include <stdio.h>
 #include <stdlib.h>
+#include <chrono>
 #include <string.h>
 #include <sys/random.h>
 #include <sstream>
@@ -67,34 +69,62 @@ Prover<Engine>::Prover(uint32_t _nVars, uint32_t _nPublic, uint32_t _domainSize,
     if (const char *e = getenv("B200_DEVICE")) first = atoi(e);
     int stride = 1;    // B200_DEVICE_STRIDE=0: all shards on one device (exercises the N-GPU host path on a 1-GPU box)
     if (const char *e = getenv("B200_DEVICE_STRIDE")) stride = atoi(e);
-    for (int g = 0; g < nGpus; g++) {
+    // one host thread per GPU: context creation, section upload (staged through pinned buffers) and the device-side
+    // CSR / table builds of the shards run side by side
+    gpus.assign(nGpus, Gpu{nullptr, nullptr});
+    std::vector<std::string> errs(nGpus);
+    std::vector<int> codes(nGpus, B200_OK);
+    const bool replicate = getenv("B200_REPLICATE_H") != nullptr;
+    const bool timing = getenv("B200_TIMING") != nullptr;
+    auto setup = [&](int g) {
+        typedef std::chrono::steady_clock clk;
+        auto t0 = clk::now();
         Gpu gp{nullptr, nullptr};
         if (b200_init(first + g * stride, &gp.ctx) != B200_OK) {
-            std::string msg = std::string("b200_init: ") + b200_last_error(nullptr);
-            for (auto &o : gpus) { b200_zkey_free(o.zk); b200_free(o.ctx); }
-            gpus.clear();
-            throw std::runtime_error(msg);
+            errs[g] = std::string("b200_init: ") + b200_last_error(nullptr);
+            codes[g] = B200_ERR_NO_GPU;
+            return;
         }
+        auto t1 = clk::now();
         // B200_PRECOMP=0|1 / B200_PRECOMP_C=<bits>: per-window tables on/off (on by default: they pay off from the
         // second proof on; the one-shot CLI turns them off itself)
         if (const char *e = getenv("B200_PRECOMP")) b200_set_option(gp.ctx, "precomp", atoi(e));
         if (const char *e = getenv("B200_PRECOMP_C")) b200_set_option(gp.ctx, "precomp_c", atoi(e));
         b200_zkey_desc d;
         d.n_vars = nVars; d.n_public = nPublic; d.domain_size = domainSize; d.n_coefs = nCoefs;
-        d.coefs = coefs; d.points_a = pointsA; d.points_b1 = pointsB1; d.points_b2 = pointsB2;
+        // shards that run none of the three transform chains (polynomial i is built on GPU i % G) never read the coefficients
+        d.coefs = (nGpus == 1 || replicate || g < 3) ? coefs : nullptr;
+        d.points_a = pointsA; d.points_b1 = pointsB1; d.points_b2 = pointsB2;
         d.points_c = pointsC; d.points_h = pointsH;
         d.shard_index = (uint32_t)g; d.shard_count = (uint32_t)nGpus;
         d.shard_lo_num = d.shard_hi_num = d.shard_den = 0;
         int rc = b200_zkey_upload(gp.ctx, &d, &gp.zk);
         if (rc != B200_OK) {
-            std::string msg = std::string("b200_zkey_upload: ") + b200_last_error(gp.ctx);
+            errs[g] = std::string("b200_zkey_upload: ") + b200_last_error(gp.ctx);
+            codes[g] = rc;
             b200_free(gp.ctx);
-            for (auto &o : gpus) { b200_zkey_free(o.zk); b200_free(o.ctx); }
-            gpus.clear();
-            if (rc == B200_ERR_RANGE) throw std::range_error("Domain size too big for the curve");
-            throw std::runtime_error(msg);
+            return;
         }
-        gpus.push_back(gp);
+        gpus[g] = gp;
+        if (timing) {
+            auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "  gpu%d: context %.1f ms, zkey upload %.1f ms\n", g, ms(t0, t1), ms(t1, clk::now()));
+        }
+    };
+    if (nGpus == 1) setup(0);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < nGpus; g++) th.emplace_back(setup, g);
+        for (auto &t : th) t.join();
+    }
+    for (int g = 0; g < nGpus; g++) {
+        if (codes[g] == B200_OK) continue;
+        std::string msg = errs[g];
+        int code = codes[g];
+        for (auto &o : gpus) { if (o.zk) b200_zkey_free(o.zk); if (o.ctx) b200_free(o.ctx); }
+        gpus.clear();
+        if (code == B200_ERR_RANGE) throw std::range_error("Domain size too big for the curve");
+        throw std::runtime_error(msg);
     }
 }
 

@@ -391,7 +391,15 @@ def test_h_pipeline_spread_over_ranks(orc, shards):
     s = synth_util.make(10)
     wt = s.wtns_bytes()
     ctxs = [b200.Context(0) for _ in range(shards)]
-    zks = [_upload(c, s, i, shards) for i, c in enumerate(ctxs)]
+    p = s.points
+    # ranks that own no chain upload the zkey WITHOUT the coefficient section (they never build a, b, c)
+    zks = [c.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section() if bdist.poly_mask(i, shards) else None,
+                         p["A"], p["B1"], p["B2"], p["C"], p["H"], i, shards) for i, c in enumerate(ctxs)]
+    if shards > 3:
+        with pytest.raises(b200.B200Error):
+            zks[shards - 1].prove_begin(wt, False, 1)          # no coefficients: cannot run a chain
+        with pytest.raises(b200.B200Error):
+            zks[shards - 1].h_scalars(wt)
     begun = [zk.prove_begin(wt, False, bdist.poly_mask(i, shards)) for i, zk in enumerate(zks)]
     dev = torch.device("cuda", 0)
     views = [[torch.as_tensor(bdist._DeviceBytes(ptr, s.n * 32), device=dev) for ptr in bufs] for bufs, _ in begun]

@@ -45,7 +45,11 @@ def main():
                            env=env, capture_output=True, text=True)
         out["b200_cli_wall_s"] = round(time.perf_counter() - t, 3)
         assert r.returncode == 0, r.stderr
-    out["b200_cli_phases"] = r.stderr.strip().splitlines()[0]
+    # stderr: "  gpu0: context X ms, zkey upload Y ms" then "open+headers .. makeProver(upload) .. prove .."
+    lines = [l.strip() for l in r.stderr.strip().splitlines()]
+    out["b200_cli_phases"] = " | ".join(l for l in lines if l.startswith("gpu0:") or l.startswith("open+headers"))
+    out["note"] = ("makeProver = CUDA context creation (a property of the box: a bare cudaFree(0) took 0.39 - 1.4 s on the "
+                   "round-2 boxes) + zkey upload (sections H2D + device-side CSR build)")
     if not args.skip_reference:
         t = time.perf_counter()
         subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_prover"), zk, wt, os.path.join(d, "p2.json"),
