@@ -1,19 +1,14 @@
-// Plain data types of the BN254 engine as the reference exposes them (depends/ffiasm/c/alt_bn128.hpp:8-60,
-// curve.hpp:11-21, f2field.hpp:7-10).  All arithmetic lives behind the C-ABI; these are layouts only.
+// The BN254 engine as the reference exposes it (depends/ffiasm/c/alt_bn128.hpp:8-60): AltBn128::Engine with its f1, f2,
+// fr, g1, g2 members, the element / point types and the global F1, F2, Fr, G1, G2 objects come from engine/alt_bn128.hpp
+// (implemented over the C-ABI: MSMs and transforms on the GPU, O(1) arithmetic on the host); this header adds the two
+// small helpers the host prover uses.
 #ifndef B200_ALT_BN128_HPP
 #define B200_ALT_BN128_HPP
 #include <stdint.h>
 #include <string>
+#include "engine/alt_bn128.hpp"
 
 namespace AltBn128 {
-
-struct FrElement { uint64_t v[4]; };
-struct F1Element { uint64_t v[4]; };
-struct F2Element { F1Element a, b; };
-struct G1PointAffine { F1Element x, y; };
-struct G2PointAffine { F2Element x, y; };
-struct G1Point { F1Element x, y, zz, zzz; };
-struct G2Point { F2Element x, y, zz, zzz; };
 
 // BN254 scalar field order r as 32 little-endian bytes (main_prover.cpp:36)
 extern const uint8_t kFrPrime[32];
@@ -22,17 +17,6 @@ extern const uint8_t kFrPrime[32];
 std::string f1ToString(const F1Element &e);
 // decimal string of a NORMAL-form 32-byte little-endian integer (public signals, main_prover.cpp:85-93)
 std::string le32ToString(const void *le32);
-
-struct Engine {
-    typedef AltBn128::FrElement FrElement;
-    typedef AltBn128::F1Element F1Element;
-    typedef AltBn128::F2Element F2Element;
-    typedef AltBn128::G1PointAffine G1PointAffine;
-    typedef AltBn128::G2PointAffine G2PointAffine;
-    typedef AltBn128::G1Point G1Point;
-    typedef AltBn128::G2Point G2Point;
-    static Engine engine;
-};
 
 }  // namespace AltBn128
 #endif

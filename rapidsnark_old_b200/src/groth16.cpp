@@ -15,7 +15,6 @@ namespace AltBn128 {
 
 const uint8_t kFrPrime[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
                               0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
-Engine Engine::engine;
 
 std::string f1ToString(const F1Element &e) {
     char buf[80];

@@ -221,6 +221,46 @@ def test_cli_output_is_byte_identical_to_reference_cli(tmp_path, gpus):
     assert (tmp_path / "public.json").read_text() == C["public_json"]
 
 
+SEAM_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_prover_b200seam")
+
+
+def _run_seam_cli(tmp_path):
+    zk, wt = tmp_path / "c.zkey", tmp_path / "w.wtns"
+    zk.write_bytes(bytes.fromhex(C["zkey"]))
+    wt.write_bytes(bytes.fromhex(C["wtns"]))
+    env = dict(os.environ, B200_R=bytes.fromhex(C["r"])[::-1].hex(), B200_S=bytes.fromhex(C["s"])[::-1].hex())
+    return subprocess.run([SEAM_CLI, str(zk), str(wt), str(tmp_path / "proof.json"), str(tmp_path / "public.json")],
+                          capture_output=True, text=True, env=env, cwd=tmp_path)
+
+
+@pytest.mark.skipif(not os.path.exists(SEAM_CLI), reason="oracle/_ref not built (no /root/reference where build() ran)")
+def test_reference_cli_builds_against_the_engine_headers_and_needs_a_gpu(tmp_path):
+    """INTEGRATION.md, inner seam: the reference's src/main_prover.cpp, groth16.cpp (through groth16.hpp), logger,
+    binfile / zkey / wtns readers - all unmodified - compiled against rapidsnark_old_b200/src/engine/ instead of
+    depends/ffiasm/c (oracle/Makefile: _ref/ref_prover_b200seam).  Without a GPU it parses the files, builds a, b, c on
+    the host and then fails at the first FFT / MSM call: there is no CPU path behind the seam."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present: the GPU test below runs it for real")
+    except ImportError:
+        pass
+    r = _run_seam_cli(tmp_path)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr or "no CPU path" in r.stderr, r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SEAM_CLI), reason="oracle/_ref not built (no /root/reference where build() ran)")
+def test_reference_cli_on_the_gpu_seam_is_byte_identical(tmp_path):
+    """The same binary on the GPU box: the reference's own prove() flow with Curve::multiMulByScalar and FFT::fft /
+    ifft served by libb200snark.so writes the reference CLI's proof.json / public.json byte for byte (same r, s)."""
+    r = _run_seam_cli(tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "proof.json").read_text() == C["proof_json"]
+    assert (tmp_path / "public.json").read_text() == C["public_json"]
+
+
 @pytest.mark.gpu
 def test_fullprover_status_machine(tmp_path):
     """FullProver (src/fullprover.cpp:21-240): ready -> busy -> success, witness from ./build/<circuit> via popen,
