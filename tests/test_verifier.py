@@ -92,3 +92,35 @@ def test_config1_reference_cli_2_10_proof_verifies(tmp_path):
     public = [int(x) for x in json.loads((tmp_path / "public.json").read_text())]
     assert public == s.wtns[1:5]
     assert pairing.groth16_verify(vk, proof, public)
+
+
+def test_verify_cli_tool_accepts_the_reference_proof_and_rejects_a_tampered_one(tmp_path):
+    """tools/verify.py = `snarkjs groth16 verify` (verification_key.json public.json proof.json -> OK! / Invalid proof,
+    exit 0 / 1), with the key exported from the zkey by tools/export_vkey.py or on the fly (--zkey)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import export_vkey
+    zk = tmp_path / "c.zkey"
+    zk.write_bytes(bytes.fromhex(C["zkey"]))
+    (tmp_path / "vk.json").write_text(json.dumps(export_vkey.export(zk.read_bytes())))
+    (tmp_path / "public.json").write_text(C["public_json"])
+    (tmp_path / "proof.json").write_text(C["proof_json"])
+    tool = [sys.executable, os.path.join(ROOT, "tools", "verify.py")]
+    r = subprocess.run(tool + [str(tmp_path / "vk.json"), str(tmp_path / "public.json"), str(tmp_path / "proof.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "OK!", r.stdout + r.stderr
+    r = subprocess.run(tool + ["--zkey", str(zk), str(tmp_path / "public.json"), str(tmp_path / "proof.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "OK!"
+    bad = json.loads(C["proof_json"])
+    bad["pi_c"][0], bad["pi_c"][1] = bad["pi_a"][0], bad["pi_a"][1]          # a valid curve point, the wrong one
+    (tmp_path / "bad.json").write_text(json.dumps(bad))
+    r = subprocess.run(tool + [str(tmp_path / "vk.json"), str(tmp_path / "public.json"), str(tmp_path / "bad.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.strip() == "Invalid proof"
+    pub = json.loads(C["public_json"])
+    (tmp_path / "pub2.json").write_text(json.dumps(pub[:-1]))
+    r = subprocess.run(tool + [str(tmp_path / "vk.json"), str(tmp_path / "pub2.json"), str(tmp_path / "proof.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 2
