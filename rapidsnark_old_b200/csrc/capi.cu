@@ -118,6 +118,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "max_batch_log2")) h->c.opt_max_batch_log2 = value;
     else if (!strcmp(name, "timeline")) h->c.opt_timeline = value;
     else if (!strcmp(name, "fuse_g1")) h->c.opt_fuse_g1 = value;
+    else if (!strcmp(name, "ntt_tma")) h->c.opt_ntt_tma = value;
     else { h->c.err = std::string("unknown option ") + name; return B200_ERR_ARG; }
     return B200_OK;
 }

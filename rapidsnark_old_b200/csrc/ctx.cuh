@@ -38,7 +38,8 @@ struct Ctx {
     cudaStream_t hstream = nullptr;    // H pipeline (a,b,c build + NTTs) overlapping the witness MSMs
     cudaEvent_t ev_h = nullptr;
     cudaEvent_t ev_xchg = nullptr;     // in-process exchange: "my peer copies of the owners' polynomials are done"
-    bool attr_ntt = false, attr_acc_staged = false;   // cudaFuncSetAttribute is per DEVICE: remembered per context
+    bool attr_ntt = false, attr_acc_staged = false, attr_ntt_tma = false;
+    int opt_ntt_tma = 0;               // 1: NTT passes move their tiles with the TMA engine (k_ntt_pass_tma)   // cudaFuncSetAttribute is per DEVICE: remembered per context
     unsigned long long peer_enabled = 0;   // devices this ctx's device has been given peer access to
     int hi_prio = 0;                   // stream priority of the side / H streams
     cudaStream_t hstream_bc[2] = {nullptr, nullptr};   // b and c transform chains beside a's (opt_h_streams = 3)

@@ -13,6 +13,9 @@
 //   DIT passes: bit-reversed in   -> natural out        (forward transform of the H pipeline)
 // so prove()'s ifft -> coset twist -> fft (src/groth16.cpp:101-155) needs no permutation pass at all;
 // the stand-alone b200_ntt_fr (natural in/out like the reference) adds one bit-reverse kernel.
+#include <cuda.h>
+#include <map>
+#include <tuple>
 #include "ctx.cuh"
 #include "memops.cuh"
 
@@ -34,6 +37,10 @@ struct NttTable {
 struct Ctx::Twiddles {
     // index [s][inverse]
     NttTable tab[29][2];
+    // twist_br[k][p] = n^-1 * w_{2n}^bitrev_k(p), n = 2^k: the factor the fused last inverse pass applies at position p
+    Fr *twist_br[29] = {nullptr};
+    // tensor maps of the TMA passes, per (array, log2 size, lo)
+    std::map<std::tuple<const void *, int, int>, CUtensorMap> tmaps;
 };
 
 DEVFN Fr lds_fr(const uint4 *p0, const uint4 *p1, u32 i) {
@@ -73,8 +80,34 @@ __global__ void __launch_bounds__(256) k_ntt_build_powers(Fr base, u32 count, Fr
 //   DIF: stages with half = H, H/2, .., H/2^(G-1); the thread owns rows  blk*2H + j + m*(2H >> G), m < 2^G
 //   DIT: stages with half = h0, 2*h0, .., h0*2^(G-1); the thread owns rows  blk*(h0 << G) + j + m*h0
 // Twiddle of a butterfly whose lower row is r at a stage of half-size `half`: w_R^((r mod half) * (R/2) / half).
-template <bool DIT, int G>
-DEVFN void ntt_group(uint4 *x0, uint4 *x1, const uint4 *w0, const uint4 *w1, u32 R, int q, u32 hsel, u32 tid, u32 nthreads) {
+// The tile in shared memory, two layouts:
+//   TilePlanes  element e = 16-byte halves at x0[e] and x1[e] (two planes: 128-bit accesses of a warp are conflict-free)
+//   TileSwz     what a TMA load with CU_TENSOR_MAP_SWIZZLE_128B leaves: rows of 128 bytes = 4 elements, the 16-byte
+//               chunk c of row r stored at chunk c ^ (r & 7); lanes on the same column of 8 consecutive rows, or on
+//               the 4 columns of 2 rows, hit 8 different chunks: conflict-free as well
+struct TilePlanes {
+    uint4 *x0, *x1;
+    DEVFN Fr ld(u32 e) const { return lds_fr(x0, x1, e); }
+    DEVFN void st(u32 e, const Fr &v) const { sts_fr(x0, x1, e, v); }
+};
+struct TileSwz {
+    uint4 *t;   // 1024-byte aligned
+    DEVFN u32 at(u32 e, u32 half) const { const u32 row = e >> 2; return row * 8 + ((((e & 3) << 1) | half) ^ (row & 7)); }
+    DEVFN Fr ld(u32 e) const {
+        Fr r;
+        uint4 a = t[at(e, 0)], b = t[at(e, 1)];
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+    DEVFN void st(u32 e, const Fr &r) const {
+        t[at(e, 0)] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        t[at(e, 1)] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    }
+};
+
+template <bool DIT, int G, class Tile>
+DEVFN void ntt_group(const Tile &X, const uint4 *w0, const uint4 *w1, u32 R, int q, u32 hsel, u32 tid, u32 nthreads) {
     const u32 Q = 1u << q;
     const u32 stride = DIT ? hsel : ((2 * hsel) >> G);      // row distance between consecutive m
     const u32 span = stride << G;                            // rows covered by one group instance
@@ -85,7 +118,7 @@ DEVFN void ntt_group(uint4 *x0, uint4 *x1, const uint4 *w0, const uint4 *w1, u32
         const u32 r0 = blk * span + j;
         Fr v[1 << G];
 #pragma unroll
-        for (int m = 0; m < (1 << G); m++) v[m] = lds_fr(x0, x1, ((r0 + m * stride) << q) + c);
+        for (int m = 0; m < (1 << G); m++) v[m] = X.ld(((r0 + m * stride) << q) + c);
 #pragma unroll
         for (int s = 0; s < G; s++) {
             const int bit = DIT ? s : (G - 1 - s);           // partner distance in m is 2^bit
@@ -112,15 +145,44 @@ DEVFN void ntt_group(uint4 *x0, uint4 *x1, const uint4 *w0, const uint4 *w1, u32
             }
         }
 #pragma unroll
-        for (int m = 0; m < (1 << G); m++) sts_fr(x0, x1, ((r0 + m * stride) << q) + c, v[m]);
+        for (int m = 0; m < (1 << G); m++) X.st(((r0 + m * stride) << q) + c, v[m]);
+    }
+}
+
+// all S butterfly stages of a tile, radix-8 steps first; every step ends with a barrier
+template <bool DIT, class Tile>
+DEVFN void ntt_stages(const Tile &X, const uint4 *w0, const uint4 *w1, u32 R, int S, int q) {
+    if (DIT) {
+        int done = 0;
+        while (S - done >= 3) { ntt_group<true, 3>(X, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 3; __syncthreads(); }
+        if (S - done == 2) { ntt_group<true, 2>(X, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 2; __syncthreads(); }
+        if (S - done == 1) { ntt_group<true, 1>(X, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 1; __syncthreads(); }
+    } else {
+        int left = S;   // stages left; the next stage has half = 2^(left-1)
+        while (left >= 3) { ntt_group<false, 3>(X, w0, w1, R, q, 1u << (left - 1), threadIdx.x, blockDim.x); left -= 3; __syncthreads(); }
+        if (left == 2) { ntt_group<false, 2>(X, w0, w1, R, q, 2u, threadIdx.x, blockDim.x); left -= 2; __syncthreads(); }
+        if (left == 1) { ntt_group<false, 1>(X, w0, w1, R, q, 1u, threadIdx.x, blockDim.x); left -= 1; __syncthreads(); }
     }
 }
 
 // One pass over HBM: tile of 2^S rows x 2^q columns in shared memory, S stages in radix-8 (then radix-4/2) steps.
 // FUSE (DIF, lo == 0 only): the ifft tail and the coset twist of groth16.cpp:107-110 are applied on the way out:
 // position p holds coefficient bitrev(p), multiplied by n^-1 * w_2n^bitrev(p).
+// twist_br[p] = n_inv * W^bitrev(p) (two-level table product), one entry per position, in the order the fused pass
+// reads it (coalesced): one product per element in that pass instead of three
+__global__ void __launch_bounds__(256) k_ntt_build_twist(Fr *__restrict__ out, int k, Fr n_inv, NttTable tb) {
+    u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >> k) return;
+    u32 i = k ? (u32)(__brevll(p) >> (64 - k)) : 0;
+    u32 ex = i << (tb.s - (k + 1));
+    Fr x = n_inv;
+    if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
+    st_struct(out + p, x);
+}
+
 template <bool DIT, bool FUSE>
-__global__ void __launch_bounds__(256, 2) k_ntt_pass(Fr *__restrict__ a, int lo, int S, int q, NttTable tb, int k, Fr n_inv) {
+__global__ void __launch_bounds__(256, 2) k_ntt_pass(Fr *__restrict__ a, int lo, int S, int q, NttTable tb, int k,
+                                                      const Fr *__restrict__ twist_br) {
     extern __shared__ uint4 smem_raw[];
     const u32 R = 1u << S, Q = 1u << q, tile_elems = R << q;
     uint4 *x0 = smem_raw, *x1 = x0 + tile_elems;
@@ -148,17 +210,7 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(Fr *__restrict__ a, int lo,
     }
     __syncthreads();
 
-    if (DIT) {
-        int done = 0;
-        while (S - done >= 3) { ntt_group<true, 3>(x0, x1, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 3; __syncthreads(); }
-        if (S - done == 2) { ntt_group<true, 2>(x0, x1, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 2; __syncthreads(); }
-        if (S - done == 1) { ntt_group<true, 1>(x0, x1, w0, w1, R, q, 1u << done, threadIdx.x, blockDim.x); done += 1; __syncthreads(); }
-    } else {
-        int left = S;   // stages left; the next stage has half = 2^(left-1)
-        while (left >= 3) { ntt_group<false, 3>(x0, x1, w0, w1, R, q, 1u << (left - 1), threadIdx.x, blockDim.x); left -= 3; __syncthreads(); }
-        if (left == 2) { ntt_group<false, 2>(x0, x1, w0, w1, R, q, 2u, threadIdx.x, blockDim.x); left -= 2; __syncthreads(); }
-        if (left == 1) { ntt_group<false, 1>(x0, x1, w0, w1, R, q, 1u, threadIdx.x, blockDim.x); left -= 1; __syncthreads(); }
-    }
+    ntt_stages<DIT>(TilePlanes{x0, x1}, w0, w1, R, S, q);
 
     for (u32 e = threadIdx.x; e < tile_elems; e += blockDim.x) {
         u32 r = e >> q, c = e & (Q - 1);
@@ -168,14 +220,109 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(Fr *__restrict__ a, int lo,
             u32 ex = ((l0 + c) * k1) << tw_shift;
             if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
         }
-        if (FUSE) {
-            u64 p = base + r;                                   // lo == 0, q == 0
-            u32 i = (u32)(__brevll(p) >> (64 - k));
-            u32 ex = i << (tb.s - (k + 1));
-            x = fp_mul(x, n_inv);
-            if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
-        }
+        if (FUSE) x = fp_mul(x, ldg_struct(twist_br + base + r));   // lo == 0, q == 0: position p = base + r
         st_struct(a + base + ((u64)r << lo) + l0 + c, x);
+    }
+}
+
+
+// ---- the same pass with the tile moved by the TMA engine ---------------------------------------------------------------
+// A strided tile (2^S rows of 4 adjacent elements, 2^lo elements apart) is a box of the array seen as a matrix with
+// rows of 2^lo elements; the contiguous tile of the lo == 0 pass is a box of the array seen as rows of 4 elements.
+// Either way: inner extent 128 bytes, up to 256 rows per cp.async.bulk.tensor, 128-byte swizzle.  One thread arms an
+// mbarrier with the tile's byte count and issues the loads; the others fetch the local twiddles meanwhile; after the
+// butterflies the tile goes back with cp.async.bulk.tensor stores.  The inter-pass twiddles, which the plain kernel
+// applies while copying, are applied in shared memory here.
+DEVFN u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+DEVFN void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+DEVFN void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVFN void mbar_wait(u64 *bar, u32 phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NTT_TMA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NTT_TMA_DONE;\n"
+        "bra NTT_TMA_WAIT;\n"
+        "NTT_TMA_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+DEVFN void tma_load_2d(void *dst, const CUtensorMap *map, u64 *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+DEVFN void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+
+template <bool DIT, bool FUSE>
+__global__ void __launch_bounds__(256, 2) k_ntt_pass_tma(const __grid_constant__ CUtensorMap map, int lo, int S, int q,
+                                                          NttTable tb, int k, const Fr *__restrict__ twist_br) {
+    extern __shared__ uint4 smem_raw[];
+    const u32 R = 1u << S, tile_elems = R << q, nrows = tile_elems >> 2;      // smem rows of 128 bytes
+    uint4 *t = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint4 *w0 = t + 2 * tile_elems, *w1 = w0 + (R >> 1);
+    u64 *bar = reinterpret_cast<u64 *>(w1 + (R >> 1));
+    const TileSwz X{t};
+
+    const u32 tiles_per_group = 1u << (lo - q);
+    const u32 tile = blockIdx.x;
+    const u64 base = (u64)(tile >> (lo - q)) << (lo + S);
+    const u32 l0 = (tile & (tiles_per_group - 1)) << q;
+    const int tw_shift = tb.s - (lo + S);
+    const u32 bh = nrows < 256 ? nrows : 256, nbox = nrows / bh;
+    // box coordinates: (u32 column, matrix row)
+    const int c0 = lo ? (int)(l0 * 8) : 0;
+    const int row0 = lo ? (int)(base >> lo) : (int)(base >> 2);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, tile_elems * 32);
+        for (u32 j = 0; j < nbox; j++) tma_load_2d(t + (size_t)j * bh * 8, &map, bar, c0, row0 + (int)(j * bh));
+    }
+    for (u32 i = threadIdx.x; i < (R >> 1); i += blockDim.x) {
+        Fr w = ldg_struct(tb.loc + ((size_t)i << (tb.loc_log - S)));
+        sts_fr(w0, w1, i, w);
+    }
+    mbar_wait(bar, 0);
+    if (DIT && lo > 0) {
+        for (u32 e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+            u32 r = e >> q, c = e & ((1u << q) - 1);
+            u32 k1 = __brev(r) >> (32 - S);
+            u32 ex = ((l0 + c) * k1) << tw_shift;
+            if (ex) X.st(e, fp_mul(X.ld(e), root_pow(tb.t_lo, tb.t_hi, tb.s, ex)));
+        }
+    }
+    __syncthreads();
+
+    ntt_stages<DIT>(X, w0, w1, R, S, q);
+
+    if ((!DIT && lo > 0) || FUSE) {
+        for (u32 e = threadIdx.x; e < tile_elems; e += blockDim.x) {
+            u32 r = e >> q, c = e & ((1u << q) - 1);
+            Fr x = X.ld(e);
+            if (!DIT && lo > 0) {
+                u32 k1 = __brev(r) >> (32 - S);
+                u32 ex = ((l0 + c) * k1) << tw_shift;
+                if (ex) x = fp_mul(x, root_pow(tb.t_lo, tb.t_hi, tb.s, ex));
+            }
+            if (FUSE) x = fp_mul(x, ldg_struct(twist_br + base + e));      // lo == 0: position p = base + e
+            X.st(e, x);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the TMA engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (u32 j = 0; j < nbox; j++) tma_store_2d(&map, t + (size_t)j * bh * 8, c0, row0 + (int)(j * bh));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -269,6 +416,7 @@ void ntt_free_tables(Ctx *ctx) {
             if (t.t_hi) cudaFree(t.t_hi);
             if (t.loc) cudaFree(t.loc);
         }
+    for (int k = 0; k < 29; k++) if (ctx->tw->twist_br[k]) cudaFree(ctx->tw->twist_br[k]);
     delete ctx->tw;
     ctx->tw = nullptr;
 }
@@ -316,9 +464,61 @@ static int ntt_plan(int k, NttPass *p) {   // passes ordered from the high bits 
     return np;
 }
 
+// 2-D view of the array for the TMA passes: rows of 2^lo elements (strided passes) or of 4 elements (lo == 0); the box
+// is 128 bytes x up to 256 rows, 128-byte swizzle.  cuTensorMapEncodeTiled comes from the driver through the runtime's
+// entry-point query, so the library does not link libcuda.
+static int ntt_tensor_map(Ctx *ctx, Fr *d_a, int k, int lo, u32 box_rows, CUtensorMap *out) {
+    auto key = std::make_tuple((const void *)d_a, k, lo * 1024 + (int)box_rows);
+    auto it = ctx->tw->tmaps.find(key);
+    if (it != ctx->tw->tmaps.end()) { *out = it->second; return B200_OK; }
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            ctx->err = "ntt: cuTensorMapEncodeTiled is not available";
+            return B200_ERR_CUDA;
+        }
+        encode = (EncodeFn)fn;
+    }
+    const int rl = lo ? lo : 2;                                   // log2 elements per matrix row
+    cuuint64_t dims[2] = {(cuuint64_t)8 << rl, (cuuint64_t)1 << (k - rl)};
+    cuuint64_t strides[1] = {(cuuint64_t)32 << rl};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->err = "ntt: cuTensorMapEncodeTiled failed"; return B200_ERR_CUDA; }
+    if (ctx->tw->tmaps.size() > 64) ctx->tw->tmaps.clear();
+    ctx->tw->tmaps[key] = m;
+    *out = m;
+    return B200_OK;
+}
+
 template <bool DIT, bool FUSE>
-static int ntt_launch_pass(Ctx *ctx, Fr *d_a, int k, const NttPass &ps, const NttTable &tb, const Fr &n_inv) {
+static int ntt_launch_pass(Ctx *ctx, Fr *d_a, int k, const NttPass &ps, const NttTable &tb, const Fr *twist_br) {
     if (ps.S == 0) return B200_OK;
+    // TMA variant (option "ntt_tma"): tiles whose shared-memory rows are whole 128-byte lines
+    if (ctx->opt_ntt_tma > 0 && k >= 12 && ((ps.lo == 0 && ps.S >= 5) || (ps.lo >= 2 && ps.q == 2))) {
+        const u32 tile_elems = 1u << (ps.S + ps.q), nrows = tile_elems >> 2, bh = nrows < 256 ? nrows : 256;
+        CUtensorMap map;
+        B200_TRY(ntt_tensor_map(ctx, d_a, k, ps.lo, bh, &map));
+        const size_t smem = (size_t)tile_elems * 32 + (size_t)(1u << (ps.S - 1)) * 32 + 16 + 1024;
+        const u32 grid = (u32)(((u64)1 << k) >> (ps.S + ps.q));
+        if (!ctx->attr_ntt_tma) {
+            B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            ctx->attr_ntt_tma = true;
+        }
+        B200_LAUNCH(ctx, (k_ntt_pass_tma<DIT, FUSE>), grid, 256, smem, map, ps.lo, ps.S, ps.q, tb, k, twist_br);
+        return B200_OK;
+    }
     const u32 tile_elems = 1u << (ps.S + ps.q);
     const size_t smem = (size_t)tile_elems * 32 + (size_t)(1u << (ps.S - 1)) * 32;
     const u32 grid = (u32)(((u64)1 << k) >> (ps.S + ps.q));
@@ -332,7 +532,7 @@ static int ntt_launch_pass(Ctx *ctx, Fr *d_a, int k, const NttPass &ps, const Nt
         B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_ntt_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         ctx->attr_ntt = true;
     }
-    B200_LAUNCH(ctx, kern, grid, threads, smem, d_a, ps.lo, ps.S, ps.q, tb, k, n_inv);
+    B200_LAUNCH(ctx, kern, grid, threads, smem, d_a, ps.lo, ps.S, ps.q, tb, k, twist_br);
     return B200_OK;
 }
 
@@ -351,17 +551,20 @@ int ntt_dif(Ctx *ctx, Fr *d_a, int k, bool inverse_roots, const Fr *n_inv = null
     B200_TRY(ntt_get_table(ctx, k, inverse_roots, &tb));
     NttPass p[8];
     int np = ntt_plan(k, p);
-    Fr one = Fr::one();
-    for (int i = 0; i < np; i++) {
-        if (n_inv && i == np - 1) {
-            // the coset twist uses FORWARD roots while the passes use inverse ones: hand the forward two-level table
-            NttTable tf, mix = tb;
+    const Fr *twist = nullptr;
+    if (n_inv) {   // table of n_inv * (FORWARD root)^bitrev(p), built once per size
+        Fr *&t = ctx->tw->twist_br[k];
+        if (!t) {
+            NttTable tf;
             B200_TRY(ntt_get_table(ctx, k, false, &tf));
-            mix.t_lo = tf.t_lo; mix.t_hi = tf.t_hi;       // last pass has lo == 0: t_lo/t_hi are only read by the twist
-            B200_TRY((ntt_launch_pass<false, true>(ctx, d_a, k, p[i], mix, *n_inv)));
-        } else {
-            B200_TRY((ntt_launch_pass<false, false>(ctx, d_a, k, p[i], tb, one)));
+            B200_CUDA_CHECK(ctx, cudaMalloc(&t, ((size_t)1 << k) * sizeof(Fr)));
+            B200_LAUNCH(ctx, k_ntt_build_twist, (u32)((((u64)1 << k) + 255) / 256), 256, 0, t, k, *n_inv, tf);
         }
+        twist = t;
+    }
+    for (int i = 0; i < np; i++) {
+        if (n_inv && i == np - 1) B200_TRY((ntt_launch_pass<false, true>(ctx, d_a, k, p[i], tb, twist)));
+        else B200_TRY((ntt_launch_pass<false, false>(ctx, d_a, k, p[i], tb, nullptr)));
     }
     return B200_OK;
 }
@@ -373,8 +576,7 @@ int ntt_dit(Ctx *ctx, Fr *d_a, int k, bool inverse_roots) {
     B200_TRY(ntt_get_table(ctx, k, inverse_roots, &tb));
     NttPass p[8];
     int np = ntt_plan(k, p);
-    Fr one = Fr::one();
-    for (int i = np - 1; i >= 0; i--) B200_TRY((ntt_launch_pass<true, false>(ctx, d_a, k, p[i], tb, one)));
+    for (int i = np - 1; i >= 0; i--) B200_TRY((ntt_launch_pass<true, false>(ctx, d_a, k, p[i], tb, nullptr)));
     return B200_OK;
 }
 

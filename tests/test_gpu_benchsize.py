@@ -83,6 +83,21 @@ def test_prove_msms_and_h_vs_reference_at_bench_size(ctx, ref, log_n, witness):
     assert ref.msms_to_affine(again) == ref.msms_to_affine(want)
 
 
+def test_h_scalars_with_tma_passes_vs_reference_2_20(ctx, ref):
+    """the H pipeline at 2^20 with option "ntt_tma" (TMA-moved tiles, strided and contiguous passes, fused twist)."""
+    s = _circuit(ctx, 20)
+    p = s.points
+    coefs, wt = s.coefs_section(), s.wtns_bytes()
+    ctx.set_option("ntt_tma", 1)
+    try:
+        zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"], p["H"])
+        got = zk.h_scalars(wt)
+        zk.free()
+    finally:
+        ctx.set_option("ntt_tma", 0)
+    assert got == ref.h_scalars(s.n, s.n_coefs, coefs, wt)
+
+
 def test_plain_tables_path_vs_reference_2_16(ctx, ref):
     """precomp = 0: the multi-window path (what the one-shot CLI runs) against the reference at 2^16."""
     s = _circuit(ctx, 16)

@@ -242,6 +242,31 @@ def test_ntt_large_roundtrip_and_oracle(ctx, orc, log_n):
         assert fwd == orc.fr_fft(data)
 
 
+@pytest.mark.parametrize("log_n", [12, 13, 14, 16, 20, 22])
+def test_ntt_tma_variant(ctx, orc, log_n):
+    """option "ntt_tma": the passes move their tiles with the TMA engine (cp.async.bulk.tensor, 128-byte swizzle,
+    mbarrier) - same bytes as the plain kernel and the oracle, forward, inverse and inside the H pipeline."""
+    import numpy as np
+    n = 1 << log_n
+    rng = np.random.default_rng(1000 + log_n)
+    data = rng.integers(0, 1 << 61, size=(n, 4), dtype=np.uint64).tobytes()
+    plain_f, plain_i = ctx.ntt(data), ctx.ntt(data, inverse=True)
+    ctx.set_option("ntt_tma", 1)
+    try:
+        tma_f, tma_i = ctx.ntt(data), ctx.ntt(data, inverse=True)
+        if log_n <= 14:
+            s = synth_util.make(log_n if log_n <= 12 else 12)
+            zk = _upload(ctx, s)
+            h = zk.h_scalars(s.wtns_bytes())
+            zk.free()
+            assert h == orc.h_scalars(s.n, s.n_coefs, s.coefs_section(), s.wtns_bytes())
+    finally:
+        ctx.set_option("ntt_tma", 0)
+    assert tma_f == plain_f and tma_i == plain_i
+    if log_n <= 16:
+        assert tma_f == orc.fr_fft(data)
+
+
 def test_ntt_domain_too_big(ctx):
     with pytest.raises(b200.B200Error):
         ctx.ntt(bytes(32 * 3))
