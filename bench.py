@@ -255,6 +255,20 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = b200.Context(local)
     log_n = args.log_n
+    if log_n >= 25:
+        # 2^26: every rank holds ~10 GB of scalar vectors, chain owners another ~9 GB of coefficient records
+        try:
+            import psutil
+            need = (12 + (10 if rank < 3 else 0)) * (1 << 30) * (1 << (log_n - 26)) * world // max(1, world // 8 or 1)
+            avail = psutil.virtual_memory().available
+            if rank == 0:
+                log("[bench] host memory: %.0f GB available, about %.0f GB needed by %d ranks" % (avail / 2**30, (12 * world + 30) * 2.0 ** (log_n - 26), world))
+            if avail < (12 * world + 30) * (1 << 30) * 2.0 ** (log_n - 26):
+                if rank == 0:
+                    print(json.dumps({"metric": "groth16_proof_ms_2^%d_constraints" % log_n, "skipped": "not enough host memory for the synthetic inputs"}), flush=True)
+                return 0
+        except ImportError:
+            pass
     # big circuits on several GPUs: every rank generates only the table slices it uploads (2^26: 24 GB of tables)
     shard_inputs = world > 1 and (args.shard_inputs or log_n >= 23)
     from rapidsnark_old_b200 import dist as bdist
@@ -279,7 +293,8 @@ def run_own(args):
             args.emulate_poly_mask = bdist.poly_mask(er, emu)
     # a rank that runs no transform chain never reads the coefficients: it uploads the zkey without section 4
     need_coefs = world == 1 or emu or args.replicate_h or bdist.poly_mask(rank, world) != 0
-    zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, s.coefs_section() if need_coefs else None, p["A"], p["B1"], p["B2"], p["C"],
+    coefs = (s.coefs_array() if hasattr(s, "coefs_array") else s.coefs_section()) if need_coefs else None   # 8.9 GB at 2^26: no copies
+    zk = ctx.zkey_upload(s.n_vars, s.n_public, s.n, s.n_coefs, coefs, p["A"], p["B1"], p["B2"], p["C"],
                          p["H"], args.emulate_rank if emu else rank, emu if emu else world, shard_bounds=bounds if (world > 1 or emu) else None)
     wt_bytes = s.wtns_bytes()
     # witness: pinned host copy (e2e) and device copy (value)
@@ -389,7 +404,7 @@ def run_own(args):
     # on the same zkey; the uniform full-width witness above is the worst case for the MSMs.  It is not a satisfying
     # assignment - the five points are checked against the known discrete logs of the tables instead.
     circom = None
-    if not emu:
+    if not emu and log_n <= 24:      # (the host-side check of this witness is Python big-integer work: minutes at 2^26)
         cw = circom_like_witness(s.n_vars)
         cw_host = torch.empty(len(cw), dtype=torch.uint8).pin_memory()
         cw_host.copy_(torch.frombuffer(bytearray(cw), dtype=torch.uint8))

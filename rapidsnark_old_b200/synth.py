@@ -269,10 +269,19 @@ class FastSynth:
         return self._wtns
 
     def coefs_section(self):
+        return self.coefs_array().tobytes()
+
+    def coefs_array(self):
+        """zkey section 4 (u32 count, then the packed 44-byte records) as ONE numpy byte buffer filled in place and
+        cached: at 2^26 the section is 8.9 GB and must not be copied around."""
         import numpy as np
+        if getattr(self, "_coefs_buf", None) is not None:
+            return self._coefs_buf
         nc, P = self.n_cons, self.n_public
         rec = np.dtype([("m", "<u4"), ("c", "<u4"), ("s", "<u4"), ("v", "V32")])
-        out = np.zeros(self.n_coefs, dtype=rec)
+        buf = np.zeros(4 + self.n_coefs * 44, dtype=np.uint8)
+        buf[:4] = np.frombuffer(struct.pack("<I", self.n_coefs & 0xffffffff), dtype=np.uint8)
+        out = buf[4:].view(rec)
         r2 = MONT * MONT % R
         one, three = (np.frombuffer((v * r2 % R).to_bytes(32, "little"), dtype="V32")[0] for v in (1, 3))
         j = np.arange(nc, dtype=np.uint32)
@@ -290,7 +299,8 @@ class FastSynth:
         tail["c"] = nc + i
         tail["s"] = i
         tail["v"] = one
-        return struct.pack("<I", self.n_coefs) + out.tobytes()
+        self._coefs_buf = buf
+        return buf
 
     build_points = Synth.build_points
 

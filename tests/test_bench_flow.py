@@ -24,6 +24,8 @@ class _FakeZKey:
         (self.n_vars, self.n_public, self.n, self.n_coefs, self.coefs, self.A, self.B1, self.B2, self.C, self.H,
          self.index, self.count) = args
         self.ctx = ctx
+        if hasattr(self.coefs, "tobytes"):
+            self.coefs = self.coefs.tobytes()       # bench hands the section over as a numpy byte buffer
         assert (self.index, self.count) == (0, 1)
 
     def _prove(self, ptr):
