@@ -359,29 +359,38 @@ def run_own(args):
         check_known_dlogs(b200, s, msms, proof, r32, s32)
 
     def timed(fn, steps, warm):
+        """ms per step over `steps` timed steps (CUDA events on the library's stream, barrier + synchronize on both
+        sides, max over ranks) - nothing but the product call inside the timed region - then the per-phase device
+        times of three more, untimed, steps (reading the phase events back is instrumentation)."""
         for _ in range(warm):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        phases = {}
         l0 = ctx.launch_count()
         e0.record(stream)
         for _ in range(steps):
             fn()
-            for k, v in ctx.phase_ms().items():
-                phases[k] = phases.get(k, 0.0) + v
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1) / steps
+        launches = (ctx.launch_count() - l0) // steps
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, {k: v / steps for k, v in phases.items()}, (ctx.launch_count() - l0) // steps
+        phases = {}
+        for _ in range(3):
+            fn()
+            for k, v in ctx.phase_ms().items():
+                phases[k] = phases.get(k, 0.0) + v / 3
+        barrier()
+        return ms, phases, launches
 
     sampler = ClockSampler(local)
     sampler.start()
+    bdist.TIMES.clear()
     ms_res, ph_res, launches = timed(step_resident, args.steps, args.warmup)
+    host_steps = {k: round(v * 1e3 / (args.steps + args.warmup + 3), 4) for k, v in bdist.TIMES.items()}   # N > 1: host ms per proof
     ms_e2e, ph_e2e, _ = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop()
 
@@ -478,6 +487,8 @@ def run_own(args):
             "phase_stream_ms": {k: round(v, 4) for k, v in ph_res.items()},
             "phase_stream_ms_e2e": {k: round(v, 4) for k, v in ph_e2e.items()},
             "timeline_ms": tls}
+    if host_steps:
+        line["host_path_ms"] = host_steps
     if emu:
         line["config"]["emulated_shards"] = emu
         line["metric"] += "_EMULATED_RANK0_OF_%d" % emu

@@ -119,18 +119,21 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "timeline")) h->c.opt_timeline = value;
     else if (!strcmp(name, "fuse_g1")) h->c.opt_fuse_g1 = value;
     else if (!strcmp(name, "ntt_tma")) h->c.opt_ntt_tma = value;
+    else if (!strcmp(name, "h_early")) h->c.opt_h_early = value;
     else { h->c.err = std::string("unknown option ") + name; return B200_ERR_ARG; }
     return B200_OK;
 }
 
 int b200_last_phase_ms(b200_ctx *h, float *out, int cap) {
     if (!h || !out) return 0;
+    phase_collect_now(&h->c);
     int k = cap < PH_COUNT ? cap : PH_COUNT;
     for (int i = 0; i < k; i++) out[i] = h->c.phase_ms[i];
     return k;
 }
 int b200_last_timeline(b200_ctx *h, float *out, int cap) {
     if (!h || !out) return 0;
+    phase_collect_now(&h->c);
     int k = (int)h->c.timeline.size();
     if (k > cap) k = cap - cap % 3;
     for (int i = 0; i < k; i++) out[i] = h->c.timeline[i];

@@ -66,6 +66,7 @@ struct Ctx {
     struct Seg { int ph, e0, e1; };
     std::vector<cudaEvent_t> evpool;   // phase timing events (reused call after call)
     std::vector<Seg> segs;
+    bool phases_pending = false;       // events of the last call recorded but not read back yet (phase_collect_now)
     int opt_timeline = 0;              // 1: phase_collect also keeps (phase, start, end) of every segment, ms from the first
     std::vector<float> timeline;       // triples, see b200_last_timeline
     int ev_used = 0;
@@ -85,6 +86,7 @@ struct Ctx {
     size_t pinned_cap = 0;
 
     void *fuse_g1 = nullptr;           // MsmFuse<Fq> of msm_g1.cu: G1 MSMs queued for one fused accumulation launch
+    int opt_h_early = -1;              // -1 auto (shards only), 0 / 1: start the H pipeline beside the witness sort instead of after it
     int opt_fuse_g1 = -1;              // -1 auto, 0 one accumulation launch per MSM, 1 fused (see prove.cu)
 
     struct SlotInfo { int nwin_b = 0, nwin = 0, c = 0, nplanes = 0, L = 0; bool used = false; } slot_info[MSM_SLOTS];
@@ -154,6 +156,7 @@ inline int phase_event(Ctx *ctx, cudaStream_t st) {
     return ctx->ev_used++;
 }
 inline void phase_reset(Ctx *ctx) {
+    ctx->phases_pending = false;
     ctx->ev_used = 0;
     ctx->segs.clear();
     for (int i = 0; i < PH_COUNT; i++) ctx->phase_ms[i] = 0.f;
@@ -166,8 +169,19 @@ inline void phase_begin(Ctx *ctx, Phase ph, cudaStream_t st = nullptr) {
     ctx->segs.push_back(s);
 }
 inline void phase_end(Ctx *ctx, cudaStream_t st = nullptr) { ctx->segs.back().e1 = phase_event(ctx, st ? st : ctx->stream); }
-inline void phase_collect(Ctx *ctx) {  // both streams must be synchronized
+// Reading the phase events back costs a few microseconds per segment (cudaEventElapsedTime): it is instrumentation,
+// not part of the call - done lazily, when somebody asks for the numbers (b200_last_phase_ms / b200_last_timeline) or
+// the next call starts, unless B200_TIMELINE wants the trace on stderr right away.
+inline void phase_collect_now(Ctx *ctx);
+inline void phase_collect(Ctx *ctx) {  // all streams must be synchronized
     static const bool timeline = getenv("B200_TIMELINE") != nullptr;
+    ctx->phases_pending = true;
+    if (timeline) phase_collect_now(ctx);
+}
+inline void phase_collect_now(Ctx *ctx) {
+    static const bool timeline = getenv("B200_TIMELINE") != nullptr;
+    if (!ctx->phases_pending) return;
+    ctx->phases_pending = false;
     if (ctx->opt_timeline) ctx->timeline.clear();
     for (auto &s : ctx->segs) {
         if (s.e1 < 0) continue;

@@ -207,8 +207,9 @@ template <class F>
 HD Affine<F> ec_to_affine(const Xyzz<F> &p) {
     Affine<F> r;
     if (p.is_zero()) { r.x = F::zero(); r.y = F::zero(); return r; }
-    r.x = fmul(p.x, finv(p.zz));
-    r.y = fmul(p.y, finv(p.zzz));
+    F i = finv(fmul(p.zz, p.zzz));            // one inversion: 1/zz = i * zzz, 1/zzz = i * zz (same canonical values)
+    r.x = fmul(p.x, fmul(i, p.zzz));
+    r.y = fmul(p.y, fmul(i, p.zz));
     return r;
 }
 

@@ -628,7 +628,8 @@ static int prove_stage1_impl(Ctx *c, b200_zkey *zk, const void *wtns, bool wtns_
     // and would only be slowed down by the NTT kernels; the G2 accumulation that follows absorbs them).  A shard of
     // several: the transform chains, the exchange and the H MSM behind them are the critical path of the proof, the
     // MSMs are short - the chains start right after the witness upload, beside the sort.
-    B200_TRY(h_on_device(c, zk, true, (lenA && !zk->sharded) ? c->ev_sort[0] : c->ev_h, poly_mask, combine));
+    const bool h_early = c->opt_h_early > 0 || (c->opt_h_early < 0 && zk->sharded);     // option "h_early"
+    B200_TRY(h_on_device(c, zk, true, (lenA && !h_early) ? c->ev_sort[0] : c->ev_h, poly_mask, combine));
     // The three witness G1 MSMs read one sorted entry list: with resident tables their accumulations go into ONE
     // launch (msm.cuh k_msm_accumulate_sets).  A single GPU that also combines here (no exchange in between) adds the
     // H MSM to the same launch in prove_enqueue_h: the H pipeline finishes under the G2 accumulation, so nothing waits.

@@ -25,7 +25,7 @@ def shard_range(length, index, count):
 # of four or eight shards it costs about twice that, measured by timing an owner rank and a non-owner rank of the
 # same world on one GPU (bench.py --emulate-shards N --emulate-rank R, profiles/r02_scaling_notes.md).
 CHAIN_COST = {2: 0.033}
-CHAIN_COST_DEFAULT = 0.07
+CHAIN_COST_DEFAULT = 0.045
 PLAN_DEN = 1 << 16
 
 
@@ -55,14 +55,39 @@ def plan_range(length, index, world, plan=None):
     return length * lo // PLAN_DEN, length * hi // PLAN_DEN
 
 
+_gather_bufs = {}   # (device, world) -> preallocated staging: pinned host in / out, device in / out
+TIMES = {}          # B200_TIMING_PY=1: accumulated host seconds per step of the N > 1 path (bench.py reports them)
+
+
+def _tick(name, t0):
+    import time
+    t1 = time.perf_counter()
+    TIMES[name] = TIMES.get(name, 0.0) + (t1 - t0)
+    return t1
+
+
 def all_gather_partials(part768, device=None, group=None):
+    """768-byte partial records of all ranks, in rank order.  On a GPU: one H2D from a pinned buffer, one
+    all_gather_into_tensor (NCCL), one D2H into a pinned buffer - all preallocated."""
     world = dist.get_world_size(group)
-    mine = torch.frombuffer(bytearray(part768), dtype=torch.uint8)
-    if device is not None:
-        mine = mine.to(device)
-    outs = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(outs, mine, group=group)
-    return [bytes(t.cpu().numpy()) for t in outs]
+    n = len(part768)
+    if device is None or torch.device(device).type != "cuda":
+        mine = torch.frombuffer(bytearray(part768), dtype=torch.uint8)
+        outs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(outs, mine, group=group)
+        return [bytes(t.numpy()) for t in outs]
+    key = (str(device), world, n)
+    if key not in _gather_bufs:
+        _gather_bufs[key] = (torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n * world, dtype=torch.uint8).pin_memory(),
+                             torch.empty(n, dtype=torch.uint8, device=device), torch.empty(n * world, dtype=torch.uint8, device=device))
+    h_in, h_out, d_in, d_out = _gather_bufs[key]
+    h_in.numpy()[:] = memoryview(part768)
+    d_in.copy_(h_in, non_blocking=True)
+    dist.all_gather_into_tensor(d_out, d_in, group=group)
+    h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    raw = h_out.numpy().tobytes()
+    return [raw[i * n:(i + 1) * n] for i in range(world)]
 
 
 def poly_owners(world):
@@ -116,8 +141,11 @@ def prove_msms_distributed(zk, wtns, on_device, domain_size, device, group=None,
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return zk.prove_msms_dev(wtns) if on_device else zk.prove_msms(wtns)
+    import time
     rank = dist.get_rank(group)
+    t = time.perf_counter()
     bufs, hstream = zk.prove_begin(wtns, on_device, poly_mask(rank, world))
+    t = _tick("prove_begin (enqueue)", t)
     key = (tuple(bufs), hstream, domain_size)
     if key not in _views:
         _views.clear()
@@ -126,14 +154,24 @@ def prove_msms_distributed(zk, wtns, on_device, domain_size, device, group=None,
     views, ext = _views[key]
     with torch.cuda.stream(ext):
         exchange_polys(views, group, plan)       # ordered after the transform kernels and before the combine, no host sync
-    return zk.prove_finish()
+    t = _tick("exchange (enqueue)", t)
+    part = zk.prove_finish()
+    _tick("prove_finish (enqueue H MSM, wait, collect)", t)
+    return part
 
 
 def finish_proof(part768, vk, r32, s32, device=None, group=None, prep640=None):
     """partial MSM results of this rank -> (folded 768-byte record, proof A|B|C 256 bytes) on every rank.
     prep640: result of groth16_blind_prepare(vk, r32, s32) computed on a host thread while the GPU worked."""
+    import time
+    t = time.perf_counter()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        part768 = fold_partials(all_gather_partials(part768, device, group))
+        parts = all_gather_partials(part768, device, group)
+        t = _tick("all_gather of the partial records", t)
+        part768 = fold_partials(parts)
     if prep640 is not None:
-        return part768, groth16_finalize_prepared(part768, vk, prep640, r32, s32)
-    return part768, groth16_finalize(part768, vk, r32, s32)
+        out = part768, groth16_finalize_prepared(part768, vk, prep640, r32, s32)
+    else:
+        out = part768, groth16_finalize(part768, vk, r32, s32)
+    _tick("fold + finalize (host)", t)
+    return out

@@ -83,8 +83,7 @@ void groth16_blind_ab(const void *pi_a128, const void *pib1_128, const void *alp
     ec_madd(pib1, b1);                                   // pib1 += beta1 + s*delta1       (:230-232)
     ec_add(pib1, sd1);
     HG1Affine pa = ec_to_affine(pi_a), pb1 = ec_to_affine(pib1);
-    HG1 t = scalar_mul(pa, s32, 32);                     // s*pi_a                         (:236-237)
-    ec_add(t, scalar_mul(pb1, r32, 32));                 // + r*pib1                       (:239-240)
+    HG1 t = double_scalar_mul(pa, s32, pb1, r32, 32);    // s*pi_a + r*pib1                (:236-240)
     memcpy(outA64, &pa, 64);
     memcpy(outT128, &t, 128);
 }
