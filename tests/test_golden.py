@@ -291,3 +291,71 @@ def test_fullprover_status_machine(tmp_path):
     r = subprocess.run([os.path.join(ROOT, "build", "fullprover_demo"), str(zk), "--", "nosuch", str(inp)],
                        capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and '"status":"failed"' in r.stdout
+
+
+@pytest.mark.gpu
+def test_proof_server_routes(tmp_path):
+    """build/proverServer <port> <zkey>: the reference's REST routes (src/main_proofserver.cpp:36-40, proverapi.cpp:9-41)
+    - GET /status, POST /input/:circuit, POST /cancel, /start, /stop - and its status documents; the proof verifies."""
+    import socket
+    import stat
+    import time
+    import urllib.request
+    import urllib.error
+    from rapidsnark_old_b200 import verify
+    sys_path_tools = os.path.join(ROOT, "tools")
+    import sys
+    sys.path.insert(0, sys_path_tools)
+    import export_vkey
+    (tmp_path / "build").mkdir()
+    zk, wt = tmp_path / "mycircuit.zkey", tmp_path / "w.wtns"
+    zk.write_bytes(bytes.fromhex(C["zkey"]))
+    wt.write_bytes(bytes.fromhex(C["wtns"]))
+    gen = tmp_path / "build" / "mycircuit"          # stand-in for the circom witness calculator binary
+    gen.write_text("#!/bin/sh\ncp %s \"$2\"\necho witness done\n" % wt)
+    gen.chmod(gen.stat().st_mode | stat.S_IEXEC)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    srv = subprocess.Popen([os.path.join(ROOT, "build", "proverServer"), str(port), str(zk)], cwd=tmp_path,
+                           env=dict(os.environ, B200_SERVER_ALLOW_QUIT="1"), stderr=subprocess.PIPE, text=True)
+    base = "http://127.0.0.1:%d" % port
+
+    def call(method, path, body=None):
+        req = urllib.request.Request(base + path, data=body, method=method)
+        with urllib.request.urlopen(req, timeout=30) as r:
+            return r.status, r.read().decode()
+    try:
+        for _ in range(600):                         # zkey upload + CUDA context creation
+            try:
+                code, text = call("GET", "/status")
+                break
+            except (urllib.error.URLError, ConnectionError):
+                assert srv.poll() is None, srv.stderr.read()
+                time.sleep(0.1)
+        assert code == 200 and json.loads(text) == {"status": "ready"}
+        assert call("POST", "/start")[0] == 200 and call("POST", "/stop")[0] == 200
+        assert call("POST", "/input/mycircuit", b'{"a": 1}')[0] == 200
+        for _ in range(600):
+            st = json.loads(call("GET", "/status")[1])
+            if st["status"] != "busy":
+                break
+            time.sleep(0.05)
+        assert st["status"] == "success", st
+        assert json.loads(st["pubData"]) == json.loads(C["public_json"])
+        assert verify.verify(export_vkey.export(zk.read_bytes()), json.loads(st["pubData"]), json.loads(st["proof"]))
+        assert call("POST", "/input/mycircuit", b'{"a": ')[0] == 200          # malformed request body
+        for _ in range(600):
+            st = json.loads(call("GET", "/status")[1])
+            if st["status"] != "busy":
+                break
+            time.sleep(0.05)
+        assert st["status"] == "failed" and "parse error" in st["error"]
+        assert call("POST", "/cancel")[0] == 200
+        with pytest.raises(urllib.error.HTTPError):
+            call("GET", "/nosuch")
+        call("POST", "/quit")
+        srv.wait(timeout=20)
+    finally:
+        if srv.poll() is None:
+            srv.kill()
