@@ -111,6 +111,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "tree_threads")) h->c.opt_tree_threads = (value == 32 || value == 64 || value == 128) ? value : 0;
     else if (!strcmp(name, "reduce_l")) h->c.opt_reduce_l = value;
     else if (!strcmp(name, "reduce_l_g2")) h->c.opt_reduce_l_g2 = value;
+    else if (!strcmp(name, "reduce_l_tail")) h->c.opt_reduce_l_tail = value;
     else if (!strcmp(name, "g2_minb")) h->c.opt_g2_minb = value;
     else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;
     else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;

@@ -70,7 +70,7 @@ inline int msm_auto_c(uint64_t n) {
 }
 
 inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool shared_buckets, int target_log2 = 0,
-                            bool tail = false) {
+                            bool tail = false, int tail_l = 0) {
     const uint64_t target_tasks = target_log2 > 0 ? (1ull << target_log2) : MSM_TARGET_TASKS;
     MsmGeom g;
     int nbits = (int)scalar_size * 8;
@@ -96,7 +96,8 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     // are short, the reduction chains are what the proof waits for (round 1, 2 / 4 shards: 16 beats 64 by 7 %;
     // round 2 with the fused accumulation launch, rank 0 of 8 / of 4: 8 beats 16 by 8 % / 2 %, 4 is worse again)
     if (shared_buckets && g.nbk < (1u << 19) && g.L > 8) g.L = 8;
-    if (tail && g.L > 16) g.L = 16;   // nothing left to overlap with: shortest chains, the whole GPU is free
+    const u32 tl = (tail_l > 0 && (tail_l & (tail_l - 1)) == 0) ? (u32)tail_l : 16u;   // option "reduce_l_tail"
+    if (tail && g.L > tl) g.L = tl;   // nothing left to overlap with: shortest chains, the whole GPU is free
     g.nseg = g.nbk / g.L;
     g.nplanes = 0;
     while ((1u << g.nplanes) < g.nseg) g.nplanes++;
@@ -732,7 +733,7 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
     const u32 batch_max = n < batch_cap ? (u32)n : batch_cap;
     int c = pre ? table->c : msm_auto_c(n);
     if (!pre && ctx->force_c >= 4 && ctx->force_c <= 20) c = ctx->force_c;
-    MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre, ctx->opt_target_tasks_log2, tail);
+    MsmGeom g = msm_geometry(batch_max, scalar_size, c, pre, ctx->opt_target_tasks_log2, tail, ctx->opt_reduce_l_tail);
     {   // experiments: reduce-segment length override ("reduce_l" both groups, "reduce_l_g2" G2 only); power of two
         int ov = (sizeof(F) != 32 && ctx->opt_reduce_l_g2 > 0) ? ctx->opt_reduce_l_g2 : ctx->opt_reduce_l;
         if (ov > 0 && (ov & (ov - 1)) == 0 && (u32)ov <= g.nbk && !(tail && ov > 16)) {

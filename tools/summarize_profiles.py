@@ -98,3 +98,19 @@ if os.path.exists(rep):
                     f.write("| %s | %s | %s |\n" % (w, d[w], d[w + "__unit"]))
             f.write("\n")
     print("accumulate metrics for", len(kernels), "launches")
+    # DRAM traffic per launch of the G1 accumulation kernel, tagged with the commit and configuration of the capture:
+    # bench.py prints it as roofline.traffic only for a run of the same configuration
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    g1 = [k for k in kernels if k["kernel"].startswith("k_msm_accumulate") and "Fq2" not in k["kernel"] and "<Fq" in k["kernel"]]
+    if g1:
+        tot = [k["dram__bytes_read.sum"] * unit[k["dram__bytes_read.sum__unit"]] +
+               k["dram__bytes_write.sum"] * unit[k["dram__bytes_write.sum__unit"]] for k in g1]
+        # the witness MSMs' launch (three MSMs) and the H launch differ in size: report the mean per launch, as
+        # bench.py's algorithmic bytes per launch are a mean as well
+        commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+        meta = {"kernel": g1[0]["kernel"], "launches_captured": len(g1), "dram_bytes_per_launch": round(sum(tot) / len(tot)),
+                "dram_bytes_each": [round(t) for t in tot], "log_n": int(os.environ.get("B200_CAPTURE_LOG_N", "20")),
+                "n_gpus": int(os.environ.get("B200_CAPTURE_GPUS", "1")), "commit": commit,
+                "command": "ncu --set full --clock-control none --import-source on -k regex:k_msm_accumulate python bench.py --steps 1 --warmup 3"}
+        json.dump(meta, open(os.path.join(dst, tag + "_accumulate_traffic.json"), "w"), indent=1)
+        print("traffic:", meta["dram_bytes_per_launch"], "bytes per launch over", len(g1), "launches")
