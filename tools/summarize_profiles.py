@@ -61,8 +61,12 @@ if os.path.exists(lc):
     print("launch summary:", len(last), "launches,", round(tot, 3), "ms")
 
 rep = os.path.join(src, tag + "_accumulate.ncu-rep")
-if os.path.exists(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = os.path.join(src, tag + "_accumulate_raw.csv")      # `ncu -i <rep> --page raw --csv`, made on the GPU box
+if os.path.exists(rep) or os.path.exists(raw):
+    if os.path.exists(raw):
+        out = open(raw).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
