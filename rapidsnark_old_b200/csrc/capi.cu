@@ -113,6 +113,8 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "reduce_l_g2")) h->c.opt_reduce_l_g2 = value;
     else if (!strcmp(name, "reduce_l_tail")) h->c.opt_reduce_l_tail = value;
     else if (!strcmp(name, "g2_minb")) h->c.opt_g2_minb = value;
+    else if (!strcmp(name, "lockstep_g1")) h->c.opt_lockstep_g1 = value;
+    else if (!strcmp(name, "lockstep_g2")) h->c.opt_lockstep_g2 = value;
     else if (!strcmp(name, "precomp")) h->c.opt_precomp = value;
     else if (!strcmp(name, "precomp_c")) h->c.opt_precomp_c = value;
     else if (!strcmp(name, "target_tasks_log2")) h->c.opt_target_tasks_log2 = value;

@@ -60,6 +60,7 @@ struct Ctx {
     int opt_reduce_l = 0, opt_reduce_l_g2 = 0;   // 0 = automatic segment length of the bucket reduction
     int opt_tree_threads = 0;   // 0 = automatic CTA size of the tree-sum kernels (power of two, 32..128)
     int opt_warm_max = 0;    // 0 = default (msm.cuh MSM_WARM_MAX)
+    int opt_lockstep_g1 = -1, opt_lockstep_g2 = 0;  // accumulation warps of a CTA in lockstep (msm.cuh k_msm_accumulate): 0 off, 1 on, G1: -1 by size (msm_lockstep_g1), G2: 2 = 256-thread CTAs
     int opt_g2_minb = 0;     // 0 auto; 2 / 3: resident CTAs per SM the G2 accumulation is compiled for (255 / 168 registers)
     int opt_precomp = -1;    // -1 auto (on), 0 off; window bits of resident tables in opt_precomp_c
     int opt_precomp_c = 0;

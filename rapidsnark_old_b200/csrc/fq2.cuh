@@ -133,6 +133,82 @@ HD u32 fq2_mul_wide(u32 *c0, u32 *c1, const Fq2T<Fq> &x, const Fq2T<Fq> &y) {
 }
 }  // namespace detail
 
+#ifndef B200_FQ2_Y3_SEQ
+#define B200_FQ2_Y3_SEQ 0
+#endif
+#if B200_FQ2_Y3_SEQ
+namespace detail {
+// 17-limb two's complement accumulators (limb 16 = sign extension): c += t / c -= t for a 16-limb t >= 0
+HD void acc17_add(u32 *c, const u32 *t) {
+    c[0] = add_cc(c[0], t[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) c[i] = addc_cc(c[i], t[i]);
+    c[16] = addc(c[16], 0);
+}
+HD void acc17_sub(u32 *c, const u32 *t) {
+    c[0] = sub_cc(c[0], t[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) c[i] = subc_cc(c[i], t[i]);
+    c[16] = subc(c[16], 0);
+}
+HD void add8_noreduce(u32 *s, const u32 *a, const u32 *b) {     // a + b < 2p < 2^255
+    s[0] = add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) s[i] = addc_cc(a[i], b[i]);
+    s[7] = addc(a[7], b[7]);
+}
+// -2 p^2 < c < 2 p^2 in two's complement -> a valid Montgomery-reduction input congruent to it
+HD void acc17_fix(u32 *c) {
+    const u32 neg = c[16];                                      // 0 or all-ones
+    c[8] = add_cc(c[8], neg & FqParams::mod(0));
+#pragma unroll
+    for (int i = 1; i < 7; i++) c[8 + i] = addc_cc(c[8 + i], neg & FqParams::mod(i));
+    c[15] = addc(c[15], neg & FqParams::mod(7));
+}
+}  // namespace detail
+
+// Same value as below, one 512-bit product alive at a time: every product is added to / subtracted from the two
+// signed accumulators as soon as it exists (the Karatsuba middle products first), so that at most c0, c1, one product
+// and one pair of operand sums are alive - 66 registers instead of 96 + operands.  For the G2 accumulation kernel
+// compiled for three CTAs per SM (168 registers), where the Y3 of the mixed addition is the register peak.
+HD Fq2T<Fq> fmul_sub_mul(const Fq2T<Fq> &x, const Fq2T<Fq> &y, const Fq2T<Fq> &z, const Fq2T<Fq> &w) {
+    u32 c0[17], c1[17], t[16];
+    {
+        u32 sa[8], sb[8];
+        detail::add8_noreduce(sa, x.a.v, x.b.v);
+        detail::add8_noreduce(sb, y.a.v, y.b.v);
+        detail::mul8x8(c1, sa, sb);                   // c1 = (xa + xb)(ya + yb)
+        c1[16] = 0;
+    }
+    detail::mul8x8(c0, x.a.v, y.a.v);                 // c0 = xa ya
+    c0[16] = 0;
+    detail::acc17_sub(c1, c0);
+    detail::mul8x8(t, x.b.v, y.b.v);
+    detail::acc17_sub(c0, t);                         // c0 = xa ya - xb yb
+    detail::acc17_sub(c1, t);                         // c1 = xa yb + xb ya
+    {
+        u32 sa[8], sb[8];
+        detail::add8_noreduce(sa, z.a.v, z.b.v);
+        detail::add8_noreduce(sb, w.a.v, w.b.v);
+        detail::mul8x8(t, sa, sb);
+        detail::acc17_sub(c1, t);
+    }
+    detail::mul8x8(t, z.a.v, w.a.v);
+    detail::acc17_sub(c0, t);
+    detail::acc17_add(c1, t);
+    detail::mul8x8(t, z.b.v, w.b.v);
+    detail::acc17_add(c0, t);                         // c0 = (xa ya - xb yb) - (za wa - zb wb)
+    detail::acc17_add(c1, t);                         // c1 = (xa yb + xb ya) - (za wb + zb wa)
+    detail::acc17_fix(c0);
+    detail::acc17_fix(c1);
+    Fq2T<Fq> r;
+    detail::mont_reduce16<FqParams>(r.a.v, c0);
+    fp_reduce_once(r.a);
+    detail::mont_reduce16<FqParams>(r.b.v, c1);
+    fp_reduce_once(r.b);
+    return r;
+}
+#else
 // |c0|, |c1| of the difference stay below 2 p^2 < p * 2^255, so one conditional + p * 2^256 makes each a valid
 // Montgomery-reduction input: 6 products and 2 reductions instead of 6 and 4
 HD Fq2T<Fq> fmul_sub_mul(const Fq2T<Fq> &x, const Fq2T<Fq> &y, const Fq2T<Fq> &z, const Fq2T<Fq> &w) {
@@ -156,6 +232,7 @@ HD Fq2T<Fq> fmul_sub_mul(const Fq2T<Fq> &x, const Fq2T<Fq> &y, const Fq2T<Fq> &z
     fp_reduce_once(r.b);
     return r;
 }
+#endif
 #endif
 
 // complex squaring, 2 base-field products (f2field.cpp:114-126)
@@ -270,6 +347,18 @@ DEVFN Fq2 hmul_sub_mul(const Fq2 &x, const Fq2 &y, const Fq2 &z, const Fq2 &w) {
     r.b = fq_reduce_call(c1);
     return r;
 }
+DEVFN Fq hmul(const Fq &x, const Fq &y) { return fmul(x, y); }
+DEVFN Fq hsqr(const Fq &x) { return fsqr(x); }
+DEVFN Fq hmul_sub_mul(const Fq &x, const Fq &y, const Fq &z, const Fq &w) { return fmul_sub_mul(x, y, z, w); }
+#elif B200_G2_HOT_CALLS == 3 && defined(__CUDA_ARCH__)
+// Variant 3: whole Fq2 products out of line with operands and result BY VALUE (registers, no stack): one copy of the
+// 3-product/2-reduction body and one of the squaring, called 6 + 2 times per mixed addition; only the fused Y3
+// (one call site) stays inlined.  Loop body ~1/4 of the inlined one (see tools/field_variants/sass_mix.py).
+static __device__ __noinline__ Fq2 fq2_mul_call(Fq2 x, Fq2 y) { return fmul(x, y); }
+static __device__ __noinline__ Fq2 fq2_sqr_call(Fq2 x) { return fsqr(x); }
+DEVFN Fq2 hmul(const Fq2 &x, const Fq2 &y) { return fq2_mul_call(x, y); }
+DEVFN Fq2 hsqr(const Fq2 &x) { return fq2_sqr_call(x); }
+DEVFN Fq2 hmul_sub_mul(const Fq2 &x, const Fq2 &y, const Fq2 &z, const Fq2 &w) { return fmul_sub_mul(x, y, z, w); }
 DEVFN Fq hmul(const Fq &x, const Fq &y) { return fmul(x, y); }
 DEVFN Fq hsqr(const Fq &x) { return fsqr(x); }
 DEVFN Fq hmul_sub_mul(const Fq &x, const Fq &y, const Fq &z, const Fq &w) { return fmul_sub_mul(x, y, z, w); }

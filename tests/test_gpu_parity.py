@@ -474,10 +474,15 @@ def test_zkey_upload_rejects_bad_records(ctx):
 
 @pytest.mark.parametrize("opts", [{"reduce_l": 16}, {"reduce_l": 4, "reduce_l_g2": 2}, {"tree_threads": 32},
                                   {"tree_threads": 128, "warm_max": 2}, {"warm_max": 64}, {"h_streams": 3},
-                                  {"g2_minb": 3}, {"log_n": 12, "reduce_l": 8, "tree_threads": 32, "warm_max": 2}])
+                                  {"g2_minb": 3}, {"log_n": 12, "reduce_l": 8, "tree_threads": 32, "warm_max": 2},
+                                  {"lockstep_g1": 1}, {"log_n": 12, "lockstep_g1": 1, "lockstep_g2": 1},
+                                  {"log_n": 12, "lockstep_g1": 0, "lockstep_g2": 2}, {"log_n": 12, "g2_minb": 3, "lockstep_g2": 1},
+                                  {"log_n": 12, "reduce_l_tail": 8}])
 def test_prove_msms_scheduling_options(ctx, orc, opts):
-    """Reduce-segment length, tree CTA size, fold threshold, transform streams, G2 occupancy variant: scheduling
-    knobs only - the five points never change.  A skewed witness makes the fold paths (warm / hot) do real work."""
+    """Reduce-segment length, tree CTA size, fold threshold, transform streams, G2 occupancy variant, lockstep
+    accumulation (one barrier per mixed addition, CTA-uniform trip count): scheduling knobs only - the five points
+    never change.  A skewed witness makes the fold paths (warm / hot) do real work and gives the tasks of one CTA
+    different lengths."""
     opts = dict(opts)
     s = synth_util.make(opts.pop("log_n", 10))    # 2^12: resident per-window tables, 2^10: plain multi-window path
     wt = bytearray(s.wtns_bytes())
@@ -495,7 +500,26 @@ def test_prove_msms_scheduling_options(ctx, orc, opts):
         zk.free()
     finally:
         for k in opts:
-            ctx.set_option(k, 0)
+            ctx.set_option(k, -1 if k == "lockstep_g1" else 0)
+
+
+@pytest.mark.parametrize("lock_g1,lock_g2", [(1, 1), (1, 2)])
+@pytest.mark.parametrize("kind", ["full", "skew"])
+def test_msm_lockstep_accumulation(ctx, orc, lock_g1, lock_g2, kind):
+    """single MSM calls (k_msm_accumulate with LOCK, 128- and 256-thread CTAs) with tasks of very different lengths
+    inside one CTA: finished threads keep arriving at the barrier, the sums are the oracle's."""
+    n = 3000
+    ctx.set_option("lockstep_g1", lock_g1)
+    ctx.set_option("lockstep_g2", lock_g2)
+    try:
+        b1, sc = _g1_points(orc, 300, 51) * 10, _scalars(n, 52, kind)
+        b2 = _g2_points(orc, 300, 53) * 10
+        got1, got2 = ctx.msm_g1(b1, sc, n), ctx.msm_g2(b2, sc, n)
+    finally:
+        ctx.set_option("lockstep_g1", -1)
+        ctx.set_option("lockstep_g2", 0)
+    assert orc.g1_to_affine(got1) == orc.g1_to_affine(orc.g1_msm(b1, sc, n))
+    assert orc.g2_to_affine(got2) == orc.g2_to_affine(orc.g2_msm(b2, sc, n))
 
 
 @pytest.mark.parametrize("precomp,pc", [(0, 0), (1, 12), (1, 16), (1, 20)])

@@ -69,17 +69,18 @@ def test_device_field_algorithm_on_host(name, p):
     assert bn.from_mont(_call("b200_host_%s_inv" % name, 32, bn.to_mont(a, p)), p) == pow(a, -1, p)
 
 
-@pytest.mark.parametrize("karatsuba,lazy", [(0, 0), (0, 1), (1, 0), (1, 1)])
-def test_field_product_variants_are_bit_exact(tmp_path, karatsuba, lazy):
+@pytest.mark.parametrize("karatsuba,lazy,y3seq", [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0), (0, 1, 1)])
+def test_field_product_variants_are_bit_exact(tmp_path, karatsuba, lazy, y3seq):
     """The build-time variants of the device products (field.cuh: Karatsuba 512-bit product, fused a*b - c*d with
     one reduction; fq2.cuh: the lazily reduced Fq2 versions) equal the word-serial Montgomery product on random and
     edge operands, and the accessor form of the mixed addition (ec_madd_acc_pt, experimental staged kernel) equals
     ec_madd including the zero / doubling / cancelling cases - host build of the same source
-    (tools/field_variants/host_test.cpp)."""
+    (tools/field_variants/host_test.cpp).  y3seq: the Fq2 x*y - z*w with one 512-bit product alive at a time
+    (fq2.cuh B200_FQ2_Y3_SEQ, measured slower on B200 and off by default)."""
     exe = tmp_path / "fv"
     src = os.path.join(ROOT, "tools", "field_variants", "host_test.cpp")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-DB200_KARATSUBA=%d" % karatsuba, "-DB200_LAZY_PAIR=%d" % lazy,
-                           "-x", "c++", src, "-o", str(exe)])
+                           "-DB200_FQ2_Y3_SEQ=%d" % y3seq, "-x", "c++", src, "-o", str(exe)])
     r = subprocess.run([str(exe), "30000"], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.count("bad=0") == 5, r.stdout + r.stderr
 
