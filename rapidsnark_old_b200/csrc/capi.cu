@@ -112,6 +112,7 @@ int b200_set_option(b200_ctx *h, const char *name, int value) {
     else if (!strcmp(name, "reduce_l")) h->c.opt_reduce_l = value;
     else if (!strcmp(name, "reduce_l_g2")) h->c.opt_reduce_l_g2 = value;
     else if (!strcmp(name, "reduce_l_tail")) h->c.opt_reduce_l_tail = value;
+    else if (!strcmp(name, "plane_items")) h->c.opt_plane_items = value;
     else if (!strcmp(name, "g2_minb")) h->c.opt_g2_minb = value;
     else if (!strcmp(name, "lockstep_g1")) h->c.opt_lockstep_g1 = value;
     else if (!strcmp(name, "lockstep_g2")) h->c.opt_lockstep_g2 = value;

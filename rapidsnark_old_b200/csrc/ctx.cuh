@@ -56,8 +56,9 @@ struct Ctx {
     int sm_count = 148;
     int force_c = 0;
     int opt_acc_smem = -1;   // -1 auto, 0 registers, 1 shared memory (experiments)
-    int opt_reduce_l_tail = 0;   // 0 = 16: segment length of an MSM's bucket reduction when nothing follows it
+    int opt_reduce_l_tail = 0;   // 0 = 32: segment length of an MSM's bucket reduction when nothing follows it
     int opt_reduce_l = 0, opt_reduce_l_g2 = 0;   // 0 = automatic segment length of the bucket reduction
+    int opt_plane_items = 0;    // 0 = 1024 segments per CTA; > 0: segments each thread of k_msm_plane_sum adds serially before the CTA tree
     int opt_tree_threads = 0;   // 0 = automatic CTA size of the tree-sum kernels (power of two, 32..128)
     int opt_warm_max = 0;    // 0 = default (msm.cuh MSM_WARM_MAX)
     int opt_lockstep_g1 = -1, opt_lockstep_g2 = 0;  // accumulation warps of a CTA in lockstep (msm.cuh k_msm_accumulate): 0 off, 1 on, G1: -1 by size (msm_lockstep_g1), G2: 2 = 256-thread CTAs

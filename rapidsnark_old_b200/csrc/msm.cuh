@@ -91,12 +91,15 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     g.CAP = cap;
     // reduce segments: longer for big bucket sets (amortises the per-segment multiplier, keeps the side-stream
     // kernel's footprint to a few dozen CTAs)
-    g.L = g.nbk >= (1u << 18) ? 64 : g.nbk >= (1u << 17) ? 32 : g.nbk >= 16 ? 16 : g.nbk;
+    // (k_msm_reduce_segments walks a segment with two lanes, L + 1 dependent additions: twice the round-1 lengths
+    // for the same chain, half the segments for the plane sums - 2^20 proof 1 % faster with 128 than with 64, 256 is
+    // 7 % slower, r02 runs 13 / 14)
+    g.L = g.nbk >= (1u << 18) ? 128 : g.nbk >= (1u << 17) ? 32 : g.nbk >= 16 ? 16 : g.nbk;
     // one shared bucket set (resident tables) below 2^19 buckets = a shard of a multi-GPU zkey: the accumulations
     // are short, the reduction chains are what the proof waits for (round 1, 2 / 4 shards: 16 beats 64 by 7 %;
     // round 2 with the fused accumulation launch, rank 0 of 8 / of 4: 8 beats 16 by 8 % / 2 %, 4 is worse again)
     if (shared_buckets && g.nbk < (1u << 19) && g.L > 8) g.L = 8;
-    const u32 tl = (tail_l > 0 && (tail_l & (tail_l - 1)) == 0) ? (u32)tail_l : 16u;   // option "reduce_l_tail"
+    const u32 tl = (tail_l > 0 && (tail_l & (tail_l - 1)) == 0) ? (u32)tail_l : 32u;   // option "reduce_l_tail" (16 and 64: 1 % slower)
     if (tail && g.L > tl) g.L = tl;   // nothing left to overlap with: shortest chains, the whole GPU is free
     g.nseg = g.nbk / g.L;
     g.nplanes = 0;
@@ -164,41 +167,61 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint8_t *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // plan[0] = partial slots allocated, plan[1] = hot buckets (> MSM_WARM_MAX tasks), plan[2] = tasks,
 // plan[3] = warm buckets (2..MSM_WARM_MAX tasks)
-static __global__ void __launch_bounds__(256) k_msm_plan_count(const u32 *__restrict__ off, u32 NB, u32 CAP,
+// Both plan kernels aggregate per CTA in shared memory first: with uniform digits every bucket holds about the same
+// number of entries, so all 2^19 buckets of a 2^20-point MSM hit the same ~40 length bins - one global atomic per
+// bucket on those few addresses cost 0.1 ms per kernel (r02 launch list), i.e. 0.2 ms of the 0.5 ms digit sort that
+// sits at the head of every proof.
+static const u32 MSM_PLAN_THREADS = 1024;
+static __global__ void __launch_bounds__(MSM_PLAN_THREADS) k_msm_plan_count(const u32 *__restrict__ off, u32 NB, u32 CAP,
                                                           u32 *__restrict__ lenhist /* [4096], index CAP_MAX - len */,
                                                           u32 *__restrict__ plan, u32 *__restrict__ hot_base,
                                                           u32 *__restrict__ hot_list, u32 *__restrict__ warm_list, u32 warm_max) {
+    __shared__ u32 sh_hist[MSM_MAX_CAP];          // bins MSM_MAX_CAP - len, len = 1 .. CAP <= MSM_MAX_CAP
+    for (u32 i = threadIdx.x; i < MSM_MAX_CAP; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= NB) return;
-    u32 cnt = off[b + 1] - off[b];
-    if (cnt == 0) return;
-    u32 nfull = cnt / CAP, rem = cnt - nfull * CAP;
-    if (nfull) atomicAdd(&lenhist[MSM_MAX_CAP - CAP], nfull);
-    if (rem) atomicAdd(&lenhist[MSM_MAX_CAP - rem], 1u);
-    u32 ntask = nfull + (rem ? 1u : 0u);
-    if (ntask > 1) {
-        hot_base[b] = atomicAdd(&plan[0], ntask);
-        if (ntask > warm_max) hot_list[atomicAdd(&plan[1], 1u)] = b;
-        else warm_list[atomicAdd(&plan[3], 1u)] = b;
+    u32 cnt = b < NB ? off[b + 1] - off[b] : 0;
+    if (cnt) {
+        u32 nfull = cnt / CAP, rem = cnt - nfull * CAP;
+        if (nfull) atomicAdd(&sh_hist[MSM_MAX_CAP - CAP], nfull);
+        if (rem) atomicAdd(&sh_hist[MSM_MAX_CAP - rem], 1u);
+        u32 ntask = nfull + (rem ? 1u : 0u);
+        if (ntask > 1) {                          // rare: a bucket of more than CAP entries
+            hot_base[b] = atomicAdd(&plan[0], ntask);
+            if (ntask > warm_max) hot_list[atomicAdd(&plan[1], 1u)] = b;
+            else warm_list[atomicAdd(&plan[3], 1u)] = b;
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < MSM_MAX_CAP; i += blockDim.x) {
+        u32 v = sh_hist[i];
+        if (v) atomicAdd(&lenhist[i], v);
     }
 }
 
-static __global__ void __launch_bounds__(256) k_msm_plan_place(const u32 *__restrict__ off, u32 NB, u32 CAP,
+static __global__ void __launch_bounds__(MSM_PLAN_THREADS) k_msm_plan_place(const u32 *__restrict__ off, u32 NB, u32 CAP,
                                                           u32 *__restrict__ cursor /* scanned lenhist */,
                                                           uint2 *__restrict__ tasks) {
+    __shared__ u32 sh_cnt[MSM_MAX_CAP], sh_base[MSM_MAX_CAP];
+    for (u32 i = threadIdx.x; i < MSM_MAX_CAP; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= NB) return;
-    u32 cnt = off[b + 1] - off[b];
-    if (cnt == 0) return;
+    u32 cnt = b < NB ? off[b + 1] - off[b] : 0;
     u32 nfull = cnt / CAP, rem = cnt - nfull * CAP;
+    u32 rank_full = 0, rank_rem = 0;              // this bucket's places inside the CTA's share of each length bin
+    if (nfull) rank_full = atomicAdd(&sh_cnt[MSM_MAX_CAP - CAP], nfull);
+    if (rem) rank_rem = atomicAdd(&sh_cnt[MSM_MAX_CAP - rem], 1u);
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < MSM_MAX_CAP; i += blockDim.x) {
+        u32 v = sh_cnt[i];
+        if (v) sh_base[i] = atomicAdd(&cursor[i], v);
+    }
+    __syncthreads();
     if (nfull) {
-        u32 pos = atomicAdd(&cursor[MSM_MAX_CAP - CAP], nfull);
+        u32 pos = sh_base[MSM_MAX_CAP - CAP] + rank_full;
         for (u32 j = 0; j < nfull; j++) tasks[pos + j] = make_uint2(b, j);
     }
-    if (rem) {
-        u32 pos = atomicAdd(&cursor[MSM_MAX_CAP - rem], 1u);
-        tasks[pos] = make_uint2(b, nfull);
-    }
+    if (rem) tasks[sh_base[MSM_MAX_CAP - rem] + rank_rem] = make_uint2(b, nfull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,25 +579,47 @@ __global__ void __launch_bounds__(128) k_msm_merge_hot(const u32 *__restrict__ o
 // Launched with 32-thread CTAs and <= 168 registers: ~5 K registers per CTA slip in next to the three resident
 // accumulation CTAs of an SM (3 x 18 K of 64 K) instead of evicting two of them, which is what a 128-thread /
 // 255-register CTA did (ncu launch list, profiles/r01_*: the reductions were 28% of the serialised time).
+// TWO lanes per segment.  The recursion  run += B_k; acc += run  is two chains of L dependent full additions of
+// which step k of the second needs only step k of the first: lane 2i walks the `run` chain and hands every new value
+// to lane 2i + 1 (warp shuffle), which adds it to `acc` one step behind - L + 1 dependent additions instead of 2 L.
+// These kernels are pure latency (10 us per dependent full addition for a lone warp; the per-MSM side streams and
+// the tail of a proof wait for exactly this chain), so halving the chain halves their duration; the number of
+// additions executed is the same.
+template <class F>
+DEVFN Xyzz<F> shfl_point(const Xyzz<F> &v, int src_lane) {
+    Xyzz<F> r;
+    const u32 *s = reinterpret_cast<const u32 *>(&v);
+    u32 *d = reinterpret_cast<u32 *>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(Xyzz<F>) / 4); i++) d[i] = __shfl_sync(0xffffffffu, s[i], src_lane);
+    return r;
+}
+
 template <class F>
 __global__ void __launch_bounds__(128, 3) k_msm_reduce_segments(const Xyzz<F> *__restrict__ buckets, u32 nbk, u32 L,
                                                                u32 nseg, u32 total_segs,
                                                                Xyzz<F> *__restrict__ seg_out) {
-    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_segs) return;
-    u32 w = g / nseg, s = g % nseg;
-    const Xyzz<F> *B = buckets + (size_t)w * nbk + (size_t)s * L;
-    Xyzz<F> run = Xyzz<F>::zero(), acc = Xyzz<F>::zero();
-    for (int k = (int)L - 1; k >= 0; k--) {
-        Xyzz<F> q = ld_struct(B + k);
-        ec_add(run, q);
-        ec_add(acc, run);
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 g = t >> 1;                         // segment; both lanes of a pair are in the same warp (t even/odd)
+    const bool second = (t & 1u) != 0;            // false: the `run` chain, true: the `acc` chain
+    const bool live = g < total_segs;             // dead pairs still take part in the shuffles
+    const u32 w = live ? g / nseg : 0, sidx = live ? g % nseg : 0;
+    const Xyzz<F> *B = buckets + (size_t)w * nbk + (size_t)sidx * L;
+    const int lane = (int)(threadIdx.x & 31u);
+    Xyzz<F> mine = Xyzz<F>::zero();               // run (first lane) or acc (second lane)
+    Xyzz<F> handed = Xyzz<F>::zero();             // second lane: `run` as it was after the previous step
+    for (int k = (int)L - 1; k >= -1; k--) {
+        Xyzz<F> q;
+        if (second) q = handed;
+        else if (live && k >= 0) q = ld_struct(B + k);
+        else q = Xyzz<F>::zero();
+        ec_add(mine, q);                          // first lane: run += B_k;  second lane: acc += run (one step behind)
+        handed = shfl_point(mine, lane & ~1);
     }
     // acc = sum (k+1) B_k over the segment (local weights), run = plain sum.  The segment starts at bucket s*L:
     // its true contribution is acc + (s*L) * run; the second term is assembled from bit-plane sums of `run`
     // over the segment index (k_msm_plane_sum) instead of a per-thread scalar multiplication.
-    st_struct(seg_out + 2 * (size_t)g, acc);
-    st_struct(seg_out + 2 * (size_t)g + 1, run);
+    if (live) st_struct(seg_out + 2 * (size_t)g + (second ? 0 : 1), mine);
 }
 
 // Bit-plane sums over the segments of one bucket set: CTA (chunk, plane, set).
@@ -729,11 +774,17 @@ int msm_post_impl(Ctx *ctx, const MsmPending<F> &p) {
     // bucket reduction + window sums + D2H on the side stream: overlaps the next MSM's sort / accumulation
     const u32 total_segs = g.nwin_b * g.nseg, npl1 = g.nplanes + 1;
     phase_begin(ctx, PH_MSM_REDUCE, side);
-    B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (total_segs + 31) / 32, 32, 0, p.d_buckets, g.nbk, g.L, g.nseg, total_segs, p.d_segs);
+    B200_LAUNCH_ON(ctx, side, k_msm_reduce_segments<F>, (2 * total_segs + 31) / 32, 32, 0, p.d_buckets, g.nbk, g.L, g.nseg, total_segs, p.d_segs);
     {
         // plane sums in two passes: nchunk CTAs per (set, plane), then one CTA per (set, plane) over the chunk sums
-        u32 nchunk = (g.nseg + 1023) / 1024;
+        // chunk size: 1024 segments per CTA = 8 (G1) / 16 (G2) per thread, added one after the other before the CTA
+        // tree.  Shorter chains (option "plane_items" = segments per thread; 2 and 4 measured on B200, r02 run 14) mean
+        // four times as many high-priority CTAs squeezing in beside the accumulation: 2 % slower on one GPU, no gain
+        // on an emulated shard
+        const u32 per_cta = ctx->opt_plane_items > 0 ? (u32)ctx->opt_plane_items * p.tree_threads : 1024u;
+        u32 nchunk = (g.nseg + per_cta - 1) / per_cta;
         if (nchunk > 128) nchunk = 128;
+        if (nchunk < 1) nchunk = 1;
         Pt *d_chunk = p.d_segs + 2 * (size_t)total_segs;
         B200_LAUNCH_ON(ctx, side, k_msm_plane_sum<F>, dim3(nchunk, npl1, g.nwin_b), p.tree_threads, p.tree_threads * sizeof(Pt), p.d_segs, g.nseg, nchunk, g.nplanes, d_chunk);
         B200_LAUNCH_ON(ctx, side, k_msm_window_sum<F>, dim3(1, npl1 * g.nwin_b), p.tree_threads, p.tree_threads * sizeof(Pt), d_chunk, nchunk, 1u, p.d_win);
@@ -893,10 +944,10 @@ int msm_enqueue_impl(Ctx *ctx, const void *d_bases_v, const void *d_scalars_v, u
             B200_LAUNCH_ON(ctx, ss, k_scan_add, ntiles, 1024, 0, d_hist, d_totals, d_cursor);
             B200_LAUNCH_ON(ctx, ss, k_msm_digits<true>, dgrid, 256, 0, sc, scalar_size, nb, g.c, g.nwin, g.nbk, pre ? 1u : 0u, tstride, d_cursor, d_entries);
             // task plan: histogram of task lengths (descending), scan, placement
-            B200_LAUNCH_ON(ctx, ss, k_msm_plan_count, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list, d_warm_list, ctx->opt_warm_max > 0 ? (u32)ctx->opt_warm_max : MSM_WARM_MAX);
+            B200_LAUNCH_ON(ctx, ss, k_msm_plan_count, (g.NB + MSM_PLAN_THREADS - 1) / MSM_PLAN_THREADS, MSM_PLAN_THREADS, 0, d_hist, g.NB, g.CAP, d_lenhist, d_plan, d_hot_base, d_hot_list, d_warm_list, ctx->opt_warm_max > 0 ? (u32)ctx->opt_warm_max : MSM_WARM_MAX);
             B200_LAUNCH_ON(ctx, ss, k_scan_tile, 1, 1024, 0, d_lenhist, d_plan + 2);      // d_plan[2] = number of tasks
             B200_CUDA_CHECK(ctx, cudaMemcpyAsync(d_lencur, d_lenhist, SCAN_TILE * 4, cudaMemcpyDeviceToDevice, ss));
-            B200_LAUNCH_ON(ctx, ss, k_msm_plan_place, (g.NB + 255) / 256, 256, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
+            B200_LAUNCH_ON(ctx, ss, k_msm_plan_place, (g.NB + MSM_PLAN_THREADS - 1) / MSM_PLAN_THREADS, MSM_PLAN_THREADS, 0, d_hist, g.NB, g.CAP, d_lencur, d_tasks);
             phase_end(ctx, ss);
             B200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_sort[ws], ss));   // "sorted": also lets callers chain other streams
             if (ss != st) B200_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_sort[ws], 0));

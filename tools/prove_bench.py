@@ -32,7 +32,7 @@ def main():
     first = None
     for cfg in args.configs:
         opts = dict(kv.split("=") for kv in cfg.split(",") if kv)
-        for k in ("precomp", "precomp_c", "acc_smem", "msm_window", "target_tasks_log2", "h_streams", "g2_minb", "warm_max", "reduce_l", "reduce_l_g2", "tree_threads", "lockstep_g1", "lockstep_g2", "fuse_g1", "h_early", "reduce_l_tail"):
+        for k in ("precomp", "precomp_c", "acc_smem", "msm_window", "target_tasks_log2", "h_streams", "g2_minb", "warm_max", "reduce_l", "reduce_l_g2", "tree_threads", "lockstep_g1", "lockstep_g2", "fuse_g1", "h_early", "reduce_l_tail", "plane_items"):
             ctx.set_option(k, int(opts.get(k, -1 if k in ("precomp", "acc_smem", "fuse_g1", "h_early", "lockstep_g1") else 0)))
         shards = int(opts.get("shards", 1))     # this GPU plays rank 0 of `shards` (per-rank time of an N-GPU run)
         t0 = time.time()
