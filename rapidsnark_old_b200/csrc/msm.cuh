@@ -98,7 +98,9 @@ inline MsmGeom msm_geometry(uint64_t n_batch, uint32_t scalar_size, int c, bool 
     // one shared bucket set (resident tables) below 2^19 buckets = a shard of a multi-GPU zkey: the accumulations
     // are short, the reduction chains are what the proof waits for (round 1, 2 / 4 shards: 16 beats 64 by 7 %;
     // round 2 with the fused accumulation launch, rank 0 of 8 / of 4: 8 beats 16 by 8 % / 2 %, 4 is worse again)
-    if (shared_buckets && g.nbk < (1u << 19) && g.L > 8) g.L = 8;
+    // round 2 with the two-lane reduction (r02 run 15, emulated rank 0 of 2 / 4 and rank 7 of 8): 16 beats 8 by
+    // 0.5 % / 1.6 % / 0.7 %, 4 is 15 % slower
+    if (shared_buckets && g.nbk < (1u << 19) && g.L > 16) g.L = 16;
     const u32 tl = (tail_l > 0 && (tail_l & (tail_l - 1)) == 0) ? (u32)tail_l : 32u;   // option "reduce_l_tail" (16 and 64: 1 % slower)
     if (tail && g.L > tl) g.L = tl;   // nothing left to overlap with: shortest chains, the whole GPU is free
     g.nseg = g.nbk / g.L;
