@@ -277,3 +277,80 @@ int main() {
             assert pyjson.loads(got) == pyjson.loads(text), (text, got)
         else:
             assert got == want, (text, got)
+
+
+def test_two_lane_bucket_reduction_schedule():
+    """The schedule of k_msm_reduce_segments (msm.cuh): lane 0 walks run += B_k, lane 1 adds the value lane 0 held
+    after the PREVIOUS step; after L + 1 steps lane 1 holds sum (k + 1) B_k and lane 0 the plain sum - the same
+    values as the one-thread recursion  run += B_k; acc += run  (multiexp.cpp:62-96 computes the same sums
+    by another recursion).  Modelled on integers: the group law is only ever used as an associative addition."""
+    r = bn.rng(11)
+    for L in (1, 2, 8, 16, 32, 128):
+        B = [r.randrange(1 << 64) if r.randrange(4) else 0 for _ in range(L)]      # a quarter of the buckets empty
+        mine = [0, 0]          # lane 0: run, lane 1: acc
+        handed = 0
+        for k in range(L - 1, -2, -1):
+            q0 = B[k] if k >= 0 else 0
+            mine = [mine[0] + q0, mine[1] + handed]
+            handed = mine[0]                                                       # shuffle from the even lane
+        run = acc = 0
+        for k in range(L - 1, -1, -1):
+            run += B[k]
+            acc += run
+        assert mine[0] == run == sum(B)
+        assert mine[1] == acc == sum((k + 1) * B[k] for k in range(L))
+
+
+def test_task_plan_cta_aggregation_model():
+    """k_msm_plan_count / k_msm_plan_place (msm.cuh) aggregate the task-length histogram and the placement ranks per
+    CTA before touching the global arrays.  Model of the two kernels + the scan between them: every task lands in a
+    distinct slot, slots are ordered by length descending, every bucket's pieces are all there."""
+    r = bn.rng(12)
+    CAP, MAXCAP, CTA = 8, 2048, 64
+    counts = [r.choice([0, 1, 3, 7, 8, 9, 20, 33]) for _ in range(1000)]
+    lenhist = [0] * MAXCAP
+    for c0 in range(0, len(counts), CTA):                      # plan_count: one shared histogram per CTA, then flushed
+        sh = {}
+        for cnt in counts[c0:c0 + CTA]:
+            if cnt:
+                nfull, rem = divmod(cnt, CAP)
+                if nfull:
+                    sh[MAXCAP - CAP] = sh.get(MAXCAP - CAP, 0) + nfull
+                if rem:
+                    sh[MAXCAP - rem] = sh.get(MAXCAP - rem, 0) + 1
+        for i, v in sh.items():
+            lenhist[i] += v
+    cursor, acc = [0] * MAXCAP, 0
+    for i in range(MAXCAP):                                    # exclusive scan: longest tasks (smallest index) first
+        cursor[i], acc = acc, acc + lenhist[i]
+    ntasks = acc
+    tasks = [None] * ntasks
+    for c0 in range(0, len(counts), CTA):                      # plan_place: local ranks, one global add per bin and CTA
+        sh_cnt, ranks = {}, []
+        for b in range(c0, min(c0 + CTA, len(counts))):
+            nfull, rem = divmod(counts[b], CAP)
+            rf = rr = None
+            if nfull:
+                rf = sh_cnt.get(MAXCAP - CAP, 0)
+                sh_cnt[MAXCAP - CAP] = rf + nfull
+            if rem:
+                rr = sh_cnt.get(MAXCAP - rem, 0)
+                sh_cnt[MAXCAP - rem] = rr + 1
+            ranks.append((b, nfull, rem, rf, rr))
+        base = {}
+        for i, v in sh_cnt.items():
+            base[i], cursor[i] = cursor[i], cursor[i] + v
+        for b, nfull, rem, rf, rr in ranks:
+            for j in range(nfull):
+                assert tasks[base[MAXCAP - CAP] + rf + j] is None
+                tasks[base[MAXCAP - CAP] + rf + j] = (b, j, CAP)
+            if rem:
+                assert tasks[base[MAXCAP - rem] + rr] is None
+                tasks[base[MAXCAP - rem] + rr] = (b, nfull, rem)
+    assert all(t is not None for t in tasks)
+    lens = [t[2] for t in tasks]
+    assert lens == sorted(lens, reverse=True)
+    per_bucket = {}
+    for b, piece, ln in tasks:
+        per_bucket.setdefault(b, []).append(ln)
+    assert all(sum(per_bucket.get(b, [])) == counts[b] for b in range(len(counts)))
