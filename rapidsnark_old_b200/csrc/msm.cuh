@@ -365,6 +365,9 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate_staged(const Affin
 #ifndef B200_G2_PREFETCH_L2
 #define B200_G2_PREFETCH_L2 1      // 1: prefetch.global.L2, 2: prefetch.global.L1 (only the 168-register G2 kernel uses it)
 #endif
+#ifndef B200_G2_PREFETCH_L2_MINB
+#define B200_G2_PREFETCH_L2_MINB 3   // from how many CTAs per SM on; 2 = also the default 255-register kernel (A/B builds)
+#endif
 DEVFN void prefetch_l2(const void *p) {
 #if B200_G2_PREFETCH_L2 == 2
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(NT, MINB) k_msm_accumulate(const Affine<F> *__
     // next point: held in registers while the current addition runs (default), or - PFL2, the G2 kernel compiled for
     // three CTAs per SM - only pulled into L2 (prefetch.global.L2: one 128-byte line = one G2 point) and loaded where it
     // is used: 32 registers fewer across the whole addition
-    constexpr bool PFL2 = B200_G2_PREFETCH_L2 && sizeof(F) != 32 && MINB >= 3;
+    constexpr bool PFL2 = B200_G2_PREFETCH_L2 && sizeof(F) != 32 && MINB >= B200_G2_PREFETCH_L2_MINB;
     u32 e_next = len ? entries[start] : 0;
     Affine<F> p_next;
     if constexpr (PFL2) prefetch_l2(bases + (e_next & 0x7fffffffu));
